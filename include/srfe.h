@@ -1,0 +1,160 @@
+/*
+ * srfe.h -- C ABI of the B200-native speech-recognition feature front end.
+ *
+ * Drop-in boundary for the acoustic feature hot path of
+ * remit0/SpeechRecognitionProject.  The reference has no FFI of its own: the
+ * boundary is five Python functions and the per-clip loops that call them
+ * (citations are into /root/reference):
+ *
+ *   srfe_spec_f32   replaces  compute_spec   models/model_spec_bgru.py:11-17
+ *                                            models/model_spec_cnn.py:12-18 (layout TF)
+ *                   + loops   models/model_spec_bgru.py:27-32, model_spec_cnn.py:38-43
+ *   srfe_fbank_f32  replaces  filter_banks   models/model_fbanks_cnn.py:15-66
+ *                   + loop    models/model_fbanks_cnn.py:84-88
+ *   srfe_mfcc_f32   replaces  compute_mfcc   models/model_mfcc_bgru.py:11-19
+ *                                            models/model_mfrn_bgru.py:11-19
+ *                   + loops   models/model_mfcc_bgru.py:29-34, model_mfrn_bgru.py:128-133
+ *   srfe_*_host_f32 the same call with HOST buffers (what Network.forward holds
+ *                   today: a CPU float32 [B,16000] batch, training.py:86), doing
+ *                   H2D -> kernel -> D2H inside the call.
+ *
+ * Conventions
+ *   - plain C, POD structs, no C++/torch types; every function returns 0
+ *     (SRFE_OK) or a negative srfe_status; srfe_last_error_string() gives the
+ *     thread-local detail.  There is NO CPU fallback: without a CUDA device the
+ *     compute entry points return SRFE_ERR_NO_DEVICE / SRFE_ERR_CUDA.
+ *   - device entry points are asynchronous and stream-ordered on `cuda_stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream); they never
+ *     synchronise and never allocate on the hot call once the (device, params)
+ *     tables exist (first call per parameter set builds and uploads them).
+ *   - the caller owns `pcm` and `out`; the library owns only immutable tables.
+ *   - pcm: float32, `n_clips` rows of `n_samples`, row stride `clip_stride`
+ *     elements (>= n_samples), int16-scale values as dataset.py:117 produces.
+ *     Rows must be 8-byte aligned (clip_stride even, base 8-byte aligned).
+ *   - out: contiguous float32, shape given by srfe_*_out_shape().
+ */
+#ifndef SRFE_H_
+#define SRFE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRFE_VERSION_MAJOR 0
+#define SRFE_VERSION_MINOR 1
+
+typedef enum srfe_status {
+    SRFE_OK = 0,
+    SRFE_ERR_BAD_ARG = -1,       /* null pointer, negative size, misaligned pointer/stride */
+    SRFE_ERR_UNSUPPORTED = -2,   /* parameter combination the kernels do not implement */
+    SRFE_ERR_CUDA = -3,          /* CUDA runtime / launch error (see error string) */
+    SRFE_ERR_NO_DEVICE = -4,     /* no CUDA device visible */
+    SRFE_ERR_TOO_LARGE = -5      /* clip too long for the fused per-clip kernels */
+} srfe_status;
+
+typedef enum srfe_layout {
+    SRFE_LAYOUT_FT = 0,          /* [clip][feature/frequency][time]  (spec_bgru, mfcc) */
+    SRFE_LAYOUT_TF = 1           /* [clip][time][feature/frequency]  (spec_cnn, fbank; GRU-ready) */
+} srfe_layout;
+
+/* log-spectrogram: scipy.signal.spectrogram(fs, nperseg, noverlap, detrend=False)
+ * with its defaults (periodic Tukey(0.25), density scaling, one-sided), then
+ * optionally ln(S + log_eps).  model_spec_bgru.py:13-14. */
+typedef struct srfe_spec_params {
+    int32_t sample_rate;         /* 16000 */
+    int32_t nperseg;             /* 640 (reference) or 512; == n_fft */
+    int32_t noverlap;            /* 320 (reference) */
+    int32_t take_log;            /* 1: ln(S + log_eps); 0: raw PSD */
+    float   log_eps;             /* 1e-10 */
+    int32_t layout;              /* srfe_layout; FT -> [B, nperseg/2+1, T], TF -> [B, T, nperseg/2+1] */
+} srfe_spec_params;
+
+/* log mel filterbank energies, model_fbanks_cnn.py:15-66 (python_speech_features
+ * style): float32 pre-emphasis, Hamming(frame_len), rfft(n_fft), |X|^2/n_fft,
+ * HTK mel triangles on floor((n_fft+1) f / fs) bins, 0 -> DBL_EPSILON, 20 log10.
+ * Output always TF: [B, T, nfilt]. */
+typedef struct srfe_fbank_params {
+    int32_t sample_rate;         /* 16000 */
+    int32_t frame_len;           /* 400 */
+    int32_t frame_step;          /* 160 */
+    int32_t n_fft;               /* 512 (or 640) ; frame_len <= n_fft */
+    float   preemph;             /* 0.97 */
+    int32_t nfilt;               /* 120 (reference), 40 (BASELINE cfg2) */
+} srfe_fbank_params;
+
+/* MFCC + deltas, model_mfcc_bgru.py:13-16 with librosa-0.6 semantics:
+ * stft(center, reflect pad, periodic Hann(win_length) centred in n_fft), |X|^2,
+ * Slaney mel (area-normalised), 10 log10(max(amin, .)), clamp to clip max - top_db,
+ * orthonormal DCT-II, np.gradient applied n_deltas times along time.
+ * Output FT: [B, (1+n_deltas)*n_mfcc, T]  or TF: [B, T, (1+n_deltas)*n_mfcc]. */
+typedef struct srfe_mfcc_params {
+    int32_t sample_rate;         /* 16000 */
+    int32_t n_fft;               /* 640 (reference) or 512 */
+    int32_t win_length;          /* <= n_fft; 0 means n_fft */
+    int32_t hop;                 /* 320 (reference) */
+    int32_t n_mels;              /* 128 */
+    float   fmin;                /* 0 */
+    float   fmax;                /* <= 0 means sample_rate / 2 */
+    int32_t n_mfcc;              /* 13 (reference), 40 (BASELINE cfg1) */
+    int32_t n_deltas;            /* 0, 1 or 2 (reference: 2) */
+    float   top_db;              /* 80; < 0 disables the clamp */
+    float   amin;                /* 1e-10 */
+    int32_t layout;              /* srfe_layout */
+} srfe_mfcc_params;
+
+/* ---- library / device ---------------------------------------------------- */
+int         srfe_version(void);                 /* major*1000 + minor */
+const char* srfe_last_error_string(void);       /* thread-local, never NULL */
+int         srfe_device_count(void);            /* >= 0, or negative srfe_status */
+
+/* ---- shapes (host only, no device needed) --------------------------------- */
+/* Writes {rows, cols} of one clip's feature matrix in the params' layout and
+ * returns the number of frames T (>= 0), or a negative srfe_status. */
+int64_t srfe_spec_out_shape (const srfe_spec_params*  p, int64_t n_samples, int64_t shape2[2]);
+int64_t srfe_fbank_out_shape(const srfe_fbank_params* p, int64_t n_samples, int64_t shape2[2]);
+int64_t srfe_mfcc_out_shape (const srfe_mfcc_params*  p, int64_t n_samples, int64_t shape2[2]);
+
+/* ---- host-side table builders (double precision; used by the kernels' table
+ *      cache and exposed so they can be verified without a GPU) -------------- */
+/* window of length n_fft as the kernels apply it (zero outside the analysis window) */
+int srfe_spec_window_f64 (const srfe_spec_params*  p, double* win /* [nperseg] */);
+int srfe_fbank_window_f64(const srfe_fbank_params* p, double* win /* [n_fft]   */);
+int srfe_mfcc_window_f64 (const srfe_mfcc_params*  p, double* win /* [n_fft]   */);
+/* dense filter matrices, row-major [n_filters][n_fft/2+1] */
+int srfe_fbank_filters_f64(const srfe_fbank_params* p, double* w);
+int srfe_mfcc_filters_f64 (const srfe_mfcc_params*  p, double* w);
+/* orthonormal DCT-II rows, row-major [n_mfcc][n_mels] */
+int srfe_mfcc_dct_f64(const srfe_mfcc_params* p, double* d);
+
+/* ---- device entry points (pcm/out are DEVICE pointers) -------------------- */
+int srfe_spec_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_spec_params* p, float* out, void* cuda_stream);
+int srfe_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_fbank_params* p, float* out, void* cuda_stream);
+int srfe_mfcc_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_mfcc_params* p, float* out, void* cuda_stream);
+
+/* ---- host entry points (pcm/out are HOST pointers; synchronous) ----------- */
+/* H2D of the batch, the same kernels, D2H of the features, on `device`.
+ * Uses a per-thread pinned staging + device workspace that grows on demand. */
+int srfe_spec_host_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_spec_params* p, float* out, int device);
+int srfe_fbank_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_fbank_params* p, float* out, int device);
+int srfe_mfcc_host_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_mfcc_params* p, float* out, int device);
+
+/* ---- introspection for benchmarks / tests --------------------------------- */
+/* number of kernel launches issued by this process through the entry points */
+int64_t srfe_launch_count(void);
+/* algorithmic bytes per clip (fp32 PCM in + fp32 features out), SURVEY.md 8d */
+int64_t srfe_spec_bytes_per_clip (const srfe_spec_params*  p, int64_t n_samples);
+int64_t srfe_fbank_bytes_per_clip(const srfe_fbank_params* p, int64_t n_samples);
+int64_t srfe_mfcc_bytes_per_clip (const srfe_mfcc_params*  p, int64_t n_samples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRFE_H_ */

@@ -1,0 +1,452 @@
+// srfe_abi.cu -- the extern "C" boundary declared in include/srfe.h: parameter
+// validation, the per-(device, parameter set) table cache, kernel launches and
+// the host-buffer entry points (H2D -> kernel -> D2H, chunked over two streams).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/srfe.h"
+#include "srfe_kernels.cuh"
+#include "srfe_tables.h"
+
+namespace srfe {
+
+static thread_local std::string g_err = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SRFE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define SRFE_CUDA(call)                                              \
+    do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+// ------------------------------------------------------------------------------
+// table cache
+// ------------------------------------------------------------------------------
+struct Entry {
+    KParams kp;                 // everything except pcm/out/sizes
+    int n_fft = 0;
+    int family = 0;
+    int blob_smem = 0;
+    void* d_blob = nullptr;
+    void* d_dct = nullptr;
+    int n_bins = 0;
+};
+
+struct Key {
+    int device, family;
+    std::string bytes;
+    bool operator<(const Key& o) const {
+        if (device != o.device) return device < o.device;
+        if (family != o.family) return family < o.family;
+        return bytes < o.bytes;
+    }
+};
+
+static std::mutex g_mu;
+static std::map<Key, Entry*> g_cache;
+static std::map<const void*, bool> g_attr_set;     // kernel function -> max-smem attribute raised (per process)
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+struct BlobBuilder {
+    std::vector<unsigned char> data;
+    int add(const void* src, size_t bytes) {
+        const int off = (int)data.size();
+        data.resize(align16(off + (int)bytes), 0);
+        if (bytes) std::memcpy(data.data() + off, src, bytes);
+        return off;
+    }
+};
+
+static void window_range(const std::vector<double>& w, int& lo, int& hi) {
+    int a = -1, b = -1;
+    for (int i = 0; i < (int)w.size(); ++i) if (w[i] != 0.0) { if (a < 0) a = i; b = i; }
+    if (a < 0) { lo = 0; hi = 0; return; }
+    lo = a & ~1;
+    hi = (b + 2) & ~1;                                   // exclusive, rounded up to even
+}
+
+static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct_t) {
+    SRFE_CUDA(cudaMalloc(&e->d_blob, bb.data.size()));
+    SRFE_CUDA(cudaMemcpy(e->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
+    if (!dct_t.empty()) {
+        SRFE_CUDA(cudaMalloc(&e->d_dct, dct_t.size() * sizeof(float)));
+        SRFE_CUDA(cudaMemcpy(e->d_dct, dct_t.data(), dct_t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    e->kp.blob = (const unsigned char*)e->d_blob;
+    e->kp.blob_bytes = (int)bb.data.size();
+    e->kp.dct_t = (const float*)e->d_dct;
+    e->blob_smem = (int)bb.data.size();
+    return SRFE_OK;
+}
+
+static void add_fft_tables(BlobBuilder& bb, KParams& kp, int n_fft, const std::vector<double>& win) {
+    std::vector<float> wf(win.begin(), win.end());
+    std::vector<F2> tw1, twu, tw16;
+    fft_twiddles(n_fft, tw1, twu, tw16);
+    kp.off_win = bb.add(wf.data(), wf.size() * 4);
+    kp.off_tw1 = bb.add(tw1.data(), tw1.size() * 8);
+    kp.off_twu = bb.add(twu.data(), twu.size() * 8);
+    kp.off_tw16 = bb.add(tw16.data(), tw16.size() * 8);
+    window_range(win, kp.w_lo, kp.w_hi);
+}
+
+static void add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb) {
+    kp.off_fs = bb.add(sb.start.data(), sb.start.size() * 4);
+    kp.off_fc = bb.add(sb.count.data(), sb.count.size() * 4);
+    kp.off_fo = bb.add(sb.offset.data(), sb.offset.size() * 4);
+    kp.off_fw = bb.add(sb.weight.data(), sb.weight.size() * 4);
+    kp.n_filt = (int)sb.start.size();
+}
+
+static int build_entry(const srfe_spec_params& p, Entry* e);
+static int build_entry(const srfe_fbank_params& p, Entry* e);
+static int build_entry(const srfe_mfcc_params& p, Entry* e);
+
+template <typename P>
+static int get_entry(int family, const P& p, Entry** out) {
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return fail(SRFE_ERR_NO_DEVICE, std::string("cudaGetDevice: ") + cudaGetErrorString(ce));
+    Key key{dev, family, std::string((const char*)&p, sizeof(P))};
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) { *out = it->second; return SRFE_OK; }
+    Entry* e = new Entry();
+    std::memset(&e->kp, 0, sizeof(KParams));
+    e->family = family;
+    int rc = build_entry(p, e);
+    if (rc != SRFE_OK) { delete e; return rc; }
+    g_cache[key] = e;
+    *out = e;
+    return SRFE_OK;
+}
+
+static int build_entry(const srfe_spec_params& p, Entry* e) {
+    std::vector<double> win;
+    spec_window(p, win);
+    double sw2 = 0.0;
+    for (double w : win) sw2 += w * w;
+    BlobBuilder bb;
+    add_fft_tables(bb, e->kp, p.nperseg, win);
+    e->n_fft = p.nperseg;
+    e->n_bins = p.nperseg / 2 + 1;
+    e->kp.hop = p.nperseg - p.noverlap;
+    e->kp.start0 = 0;
+    e->kp.scale = (float)(0.25 / ((double)p.sample_rate * sw2));   // density scaling; 1/4 from the untangle
+    e->kp.log_eps = p.log_eps;
+    e->kp.take_log = p.take_log;
+    e->kp.layout = p.layout;
+    return upload(e, bb, {});
+}
+
+static int build_entry(const srfe_fbank_params& p, Entry* e) {
+    std::vector<double> win, dense;
+    fbank_window(p, win);
+    fbank_filters(p, dense);
+    SparseBank sb;
+    to_sparse(dense, p.nfilt, p.n_fft / 2 + 1, 0.25 / (double)p.n_fft, sb);   // |X|^2 / NFFT (model_fbanks_cnn.py:43)
+    BlobBuilder bb;
+    add_fft_tables(bb, e->kp, p.n_fft, win);
+    add_bank(bb, e->kp, sb);
+    e->n_fft = p.n_fft;
+    e->n_bins = p.n_fft / 2 + 1;
+    e->kp.hop = p.frame_step;
+    e->kp.start0 = 0;
+    e->kp.preemph = p.preemph;
+    e->kp.layout = SRFE_LAYOUT_TF;
+    return upload(e, bb, {});
+}
+
+static int build_entry(const srfe_mfcc_params& p, Entry* e) {
+    std::vector<double> win, dense, dct;
+    mfcc_window(p, win);
+    mfcc_filters(p, dense);
+    mfcc_dct(p, dct);
+    SparseBank sb;
+    to_sparse(dense, p.n_mels, p.n_fft / 2 + 1, 0.25, sb);
+    BlobBuilder bb;
+    add_fft_tables(bb, e->kp, p.n_fft, win);
+    add_bank(bb, e->kp, sb);
+    e->n_fft = p.n_fft;
+    e->n_bins = p.n_fft / 2 + 1;
+    e->kp.hop = p.hop;
+    e->kp.start0 = -(p.n_fft / 2);
+    e->kp.n_mfcc = p.n_mfcc;
+    e->kp.n_mfcc_pad = (p.n_mfcc + 3) & ~3;
+    e->kp.n_deltas = p.n_deltas;
+    e->kp.top_db = p.top_db;
+    e->kp.amin = p.amin;
+    e->kp.layout = p.layout;
+    e->kp.tile_stride = p.n_mels | 1;                                  // odd: conflict-free column reads
+    std::vector<float> dct_t((size_t)p.n_mels * e->kp.n_mfcc_pad, 0.f);
+    for (int k = 0; k < p.n_mfcc; ++k)
+        for (int f = 0; f < p.n_mels; ++f) dct_t[(size_t)f * e->kp.n_mfcc_pad + k] = (float)dct[(size_t)k * p.n_mels + f];
+    return upload(e, bb, dct_t);
+}
+
+// ------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------
+template <int NFFT, int FAM>
+static int launch_t(const KParams& kp, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_kernel<NFFT, FAM>;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const void* tag = (const char*)(const void*)kern + dev;      // per (kernel, device)
+        if (!g_attr_set.count(tag)) {
+            SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            g_attr_set[tag] = true;
+        }
+    }
+    srfe_kernel<NFFT, FAM><<<kp.n_clips, kThreads, smem_bytes, st>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_kernel launch");
+    g_launches.fetch_add(1);
+    return SRFE_OK;
+}
+
+static int launch(const Entry* e, KParams kp, cudaStream_t st) {
+    const int scratch = kSlots * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
+    int tile = 0;
+    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT) tile = e->n_bins * kSpecTileStride * 4;
+    if (e->family == FAM_MFCC) {
+        tile = kp.T * kp.tile_stride * 4;
+        const int TC = kp.T + 1;
+        if (kp.n_mfcc * TC * 4 > scratch || (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile))
+            return fail(SRFE_ERR_TOO_LARGE, "mfcc: coefficient tile does not fit the per-clip shared memory budget");
+        if (kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
+    }
+    kp.sm_scratch = align16(e->blob_smem);
+    kp.sm_tile = kp.sm_scratch + scratch;
+    const int smem = kp.sm_tile + align16(tile);
+    if (smem > 200 * 1024) return fail(SRFE_ERR_TOO_LARGE, "clip too long: per-clip tile exceeds shared memory");
+    if (kp.n_clips == 0) return SRFE_OK;
+#define SRFE_DISPATCH(N)                                                       \
+    switch (e->family) {                                                       \
+        case FAM_SPEC: return launch_t<N, FAM_SPEC>(kp, smem, st);             \
+        case FAM_FBANK: return launch_t<N, FAM_FBANK>(kp, smem, st);           \
+        default: return launch_t<N, FAM_MFCC>(kp, smem, st);                   \
+    }
+    if (e->n_fft == 512) { SRFE_DISPATCH(512) } else { SRFE_DISPATCH(640) }
+#undef SRFE_DISPATCH
+}
+
+static int check_buffers(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const void* p,
+                         const float* out) {
+    if (!p) return fail(SRFE_ERR_BAD_ARG, "params is NULL");
+    if (n_clips < 0 || n_samples <= 0) return fail(SRFE_ERR_BAD_ARG, "n_clips must be >= 0 and n_samples > 0");
+    if (n_clips > 0 && (!pcm || !out)) return fail(SRFE_ERR_BAD_ARG, "pcm/out is NULL");
+    if (clip_stride < n_samples) return fail(SRFE_ERR_BAD_ARG, "clip_stride < n_samples");
+    if (n_clips > 1 && (clip_stride & 1)) return fail(SRFE_ERR_BAD_ARG, "clip_stride must be even (8-byte aligned rows)");
+    if (((uintptr_t)pcm & 7) || ((uintptr_t)out & 3)) return fail(SRFE_ERR_BAD_ARG, "pcm must be 8-byte aligned, out 4-byte aligned");
+    if (n_clips > 0x7fffffffLL || n_samples > (1 << 24)) return fail(SRFE_ERR_TOO_LARGE, "n_clips / n_samples too large");
+    return SRFE_OK;
+}
+
+template <typename P>
+static int run_device(int family, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const P* p,
+                      float* out, cudaStream_t st, int64_t T) {
+    Entry* e = nullptr;
+    int rc = get_entry(family, *p, &e);
+    if (rc != SRFE_OK) return rc;
+    KParams kp = e->kp;
+    kp.pcm = pcm;
+    kp.out = out;
+    kp.clip_stride = clip_stride;
+    kp.n_clips = (int)n_clips;
+    kp.n_samples = (int)n_samples;
+    kp.T = (int)T;
+    return launch(e, kp, st);
+}
+
+// ------------------------------------------------------------------------------
+// host-buffer path: chunked H2D -> kernel -> D2H on two streams
+// ------------------------------------------------------------------------------
+struct HostWs {
+    int device = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    float* d_in[2] = {nullptr, nullptr};
+    float* d_out[2] = {nullptr, nullptr};
+    size_t cap_in = 0, cap_out = 0;
+};
+static thread_local HostWs g_ws[16];
+
+static int host_ws(int device, size_t in_bytes, size_t out_bytes, HostWs** out) {
+    if (device < 0 || device >= 16) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
+    HostWs& w = g_ws[device];
+    if (w.device < 0) {
+        for (int i = 0; i < 2; ++i) SRFE_CUDA(cudaStreamCreateWithFlags(&w.st[i], cudaStreamNonBlocking));
+        w.device = device;
+    }
+    if (in_bytes > w.cap_in) {
+        for (int i = 0; i < 2; ++i) { if (w.d_in[i]) cudaFree(w.d_in[i]); SRFE_CUDA(cudaMalloc(&w.d_in[i], in_bytes)); }
+        w.cap_in = in_bytes;
+    }
+    if (out_bytes > w.cap_out) {
+        for (int i = 0; i < 2; ++i) { if (w.d_out[i]) cudaFree(w.d_out[i]); SRFE_CUDA(cudaMalloc(&w.d_out[i], out_bytes)); }
+        w.cap_out = out_bytes;
+    }
+    *out = &w;
+    return SRFE_OK;
+}
+
+template <typename P>
+static int run_host(int family, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const P* p,
+                    float* out, int device, int64_t T, int64_t out_per_clip) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) return fail(SRFE_ERR_NO_DEVICE, "no CUDA device");
+    SRFE_CUDA(cudaSetDevice(device));
+    const int64_t chunk = n_clips < 2048 ? (n_clips > 0 ? n_clips : 1) : 2048;
+    HostWs* w = nullptr;
+    int rc = host_ws(device, (size_t)chunk * n_samples * 4, (size_t)chunk * out_per_clip * 4, &w);
+    for (int64_t c0 = 0, i = 0; rc == SRFE_OK && c0 < n_clips; c0 += chunk, ++i) {
+        const int64_t nc = (n_clips - c0 < chunk) ? n_clips - c0 : chunk;
+        const int s = (int)(i & 1);
+        cudaError_t ce = cudaMemcpy2DAsync(w->d_in[s], (size_t)n_samples * 4, pcm + c0 * clip_stride, (size_t)clip_stride * 4,
+                                           (size_t)n_samples * 4, (size_t)nc, cudaMemcpyHostToDevice, w->st[s]);
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D"); break; }
+        rc = run_device(family, w->d_in[s], nc, n_samples, n_samples, p, w->d_out[s], w->st[s], T);
+        if (rc != SRFE_OK) break;
+        ce = cudaMemcpyAsync(out + c0 * out_per_clip, w->d_out[s], (size_t)nc * out_per_clip * 4, cudaMemcpyDeviceToHost, w->st[s]);
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "D2H"); break; }
+    }
+    if (w) for (int i = 0; i < 2; ++i) {
+        cudaError_t ce = cudaStreamSynchronize(w->st[i]);
+        if (ce != cudaSuccess && rc == SRFE_OK) rc = cuda_fail(ce, "cudaStreamSynchronize");
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+}  // namespace srfe
+
+using namespace srfe;
+
+// ------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------
+extern "C" {
+
+int srfe_version(void) { return SRFE_VERSION_MAJOR * 1000 + SRFE_VERSION_MINOR; }
+const char* srfe_last_error_string(void) { return g_err.c_str(); }
+int srfe_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SRFE_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+    return n;
+}
+int64_t srfe_launch_count(void) { return g_launches.load(); }
+
+#define SRFE_VALIDATE(p)                                            \
+    if (!(p)) return fail(SRFE_ERR_BAD_ARG, "params is NULL");      \
+    { const char* why = ""; int rc__ = validate(*(p), &why); if (rc__ != SRFE_OK) return fail(rc__, why); }
+
+int64_t srfe_spec_out_shape(const srfe_spec_params* p, int64_t n, int64_t shape2[2]) {
+    SRFE_VALIDATE(p)
+    if (n < p->nperseg) return fail(SRFE_ERR_BAD_ARG, "spec: n_samples < nperseg");
+    const int64_t T = spec_frames(*p, n), F = p->nperseg / 2 + 1;
+    if (shape2) { shape2[0] = p->layout == SRFE_LAYOUT_FT ? F : T; shape2[1] = p->layout == SRFE_LAYOUT_FT ? T : F; }
+    return T;
+}
+int64_t srfe_fbank_out_shape(const srfe_fbank_params* p, int64_t n, int64_t shape2[2]) {
+    SRFE_VALIDATE(p)
+    if (n < 1) return fail(SRFE_ERR_BAD_ARG, "fbank: n_samples < 1");
+    const int64_t T = fbank_frames(*p, n);
+    if (shape2) { shape2[0] = T; shape2[1] = p->nfilt; }
+    return T;
+}
+int64_t srfe_mfcc_out_shape(const srfe_mfcc_params* p, int64_t n, int64_t shape2[2]) {
+    SRFE_VALIDATE(p)
+    if (n <= p->n_fft / 2) return fail(SRFE_ERR_BAD_ARG, "mfcc: reflect padding needs n_samples > n_fft/2");
+    const int64_t T = mfcc_frames(*p, n), R = (int64_t)(1 + p->n_deltas) * p->n_mfcc;
+    if (shape2) { shape2[0] = p->layout == SRFE_LAYOUT_FT ? R : T; shape2[1] = p->layout == SRFE_LAYOUT_FT ? T : R; }
+    return T;
+}
+
+int64_t srfe_spec_bytes_per_clip(const srfe_spec_params* p, int64_t n) {
+    int64_t s[2]; const int64_t T = srfe_spec_out_shape(p, n, s);
+    return T < 0 ? T : n * 4 + s[0] * s[1] * 4;
+}
+int64_t srfe_fbank_bytes_per_clip(const srfe_fbank_params* p, int64_t n) {
+    int64_t s[2]; const int64_t T = srfe_fbank_out_shape(p, n, s);
+    return T < 0 ? T : n * 4 + s[0] * s[1] * 4;
+}
+int64_t srfe_mfcc_bytes_per_clip(const srfe_mfcc_params* p, int64_t n) {
+    int64_t s[2]; const int64_t T = srfe_mfcc_out_shape(p, n, s);
+    return T < 0 ? T : n * 4 + s[0] * s[1] * 4;
+}
+
+static int copy_out(const std::vector<double>& v, double* dst) {
+    if (!dst) return fail(SRFE_ERR_BAD_ARG, "output pointer is NULL");
+    std::memcpy(dst, v.data(), v.size() * sizeof(double));
+    return SRFE_OK;
+}
+int srfe_spec_window_f64(const srfe_spec_params* p, double* win) { SRFE_VALIDATE(p) std::vector<double> w; spec_window(*p, w); return copy_out(w, win); }
+int srfe_fbank_window_f64(const srfe_fbank_params* p, double* win) { SRFE_VALIDATE(p) std::vector<double> w; fbank_window(*p, w); return copy_out(w, win); }
+int srfe_mfcc_window_f64(const srfe_mfcc_params* p, double* win) { SRFE_VALIDATE(p) std::vector<double> w; mfcc_window(*p, w); return copy_out(w, win); }
+int srfe_fbank_filters_f64(const srfe_fbank_params* p, double* w) { SRFE_VALIDATE(p) std::vector<double> d; fbank_filters(*p, d); return copy_out(d, w); }
+int srfe_mfcc_filters_f64(const srfe_mfcc_params* p, double* w) { SRFE_VALIDATE(p) std::vector<double> d; mfcc_filters(*p, d); return copy_out(d, w); }
+int srfe_mfcc_dct_f64(const srfe_mfcc_params* p, double* d) { SRFE_VALIDATE(p) std::vector<double> v; mfcc_dct(*p, v); return copy_out(v, d); }
+
+int srfe_spec_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_spec_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_SPEC, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+int srfe_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
+                   float* out, void* stream) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_fbank_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_FBANK, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+int srfe_mfcc_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_mfcc_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_MFCC, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+
+int srfe_spec_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
+                       float* out, int device) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_spec_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_SPEC, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_fbank_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
+                        float* out, int device) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_fbank_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_FBANK, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_mfcc_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
+                       float* out, int device) {
+    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_mfcc_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_MFCC, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's feature interface, backed by libsrfe.so.
+
+Reference interface (citations into /root/reference):
+
+* ``compute_spec(sample)``  models/model_spec_bgru.py:11-17 -> FloatTensor[321,49]
+                            models/model_spec_cnn.py:12-18  -> FloatTensor[49,321]
+* ``filter_banks(sample)``  models/model_fbanks_cnn.py:15-66 -> FloatTensor[98,120]
+* ``compute_mfcc(sample)``  models/model_mfcc_bgru.py:11-19  -> FloatTensor[39,51]
+  (``sample`` = 1-D float32 tensor of 16000 int16-scale samples, dataset.py:117)
+
+plus the batched forms that replace the per-clip loops of ``Network.forward``
+(model_mfcc_bgru.py:29-34 etc.): ``spec(x[B,N])``, ``fbank(x)``, ``mfcc(x)``.
+
+Compute always happens in the CUDA kernels: CUDA tensors go through the
+``srfe::*`` custom ops (stream-ordered, no sync); CPU tensors go through the
+``srfe_*_host_f32`` entry points (H2D -> kernel -> D2H) and come back on the CPU,
+like the reference's return values.  There is no CPU implementation here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, replace
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_FT, LAYOUT_TF, FbankParamsC, MfccParamsC, SpecParamsC
+
+__all__ = [
+    "SpecParams", "FbankParams", "MfccParams", "PRESETS",
+    "R_SPEC", "C_SPEC", "R_FBANK", "C_FBANK", "R_MFCC", "C_MFCC", "C_MFCC_D2",
+    "spec", "fbank", "mfcc", "compute_spec", "filter_banks", "compute_mfcc",
+    "out_shape", "bytes_per_clip", "launch_count",
+]
+
+
+def _layout_code(layout: str) -> int:
+    if layout not in ("ft", "tf"):
+        raise ValueError("layout must be 'ft' ([B, feature, time]) or 'tf' ([B, time, feature])")
+    return LAYOUT_FT if layout == "ft" else LAYOUT_TF
+
+
+@dataclass(frozen=True)
+class SpecParams:
+    """scipy.signal.spectrogram call of model_spec_bgru.py:13-14, literals lifted."""
+    fs: int = 16000
+    nperseg: int = 640
+    noverlap: int = 320
+    log: bool = True
+    eps: float = 1e-10
+    layout: str = "ft"
+
+    def to_c(self) -> SpecParamsC:
+        return SpecParamsC(self.fs, self.nperseg, self.noverlap, int(self.log), self.eps, _layout_code(self.layout))
+
+
+@dataclass(frozen=True)
+class FbankParams:
+    """model_fbanks_cnn.py:18-45 literals, lifted."""
+    fs: int = 16000
+    frame_len: int = 400
+    frame_step: int = 160
+    nfft: int = 512
+    preemph: float = 0.97
+    nfilt: int = 120
+
+    def to_c(self) -> FbankParamsC:
+        return FbankParamsC(self.fs, self.frame_len, self.frame_step, self.nfft, self.preemph, self.nfilt)
+
+
+@dataclass(frozen=True)
+class MfccParams:
+    """librosa.feature.mfcc call of model_mfcc_bgru.py:13 (+ librosa-0.6 defaults) and
+    the two np.gradient passes of :14-16."""
+    sr: int = 16000
+    n_fft: int = 640
+    win_length: Optional[int] = None
+    hop: int = 320
+    n_mels: int = 128
+    fmin: float = 0.0
+    fmax: Optional[float] = None
+    n_mfcc: int = 13
+    n_deltas: int = 2
+    top_db: Optional[float] = 80.0
+    amin: float = 1e-10
+    layout: str = "ft"
+
+    def to_c(self) -> MfccParamsC:
+        return MfccParamsC(self.sr, self.n_fft, self.win_length or 0, self.hop, self.n_mels, self.fmin,
+                           self.fmax if self.fmax else 0.0, self.n_mfcc, self.n_deltas,
+                           -1.0 if self.top_db is None else self.top_db, self.amin, _layout_code(self.layout))
+
+
+R_SPEC = SpecParams()
+C_SPEC = SpecParams(nperseg=512, noverlap=256)
+R_FBANK = FbankParams()
+C_FBANK = FbankParams(nfilt=40)
+R_MFCC = MfccParams()
+C_MFCC = MfccParams(n_fft=512, win_length=400, hop=160, n_mfcc=40, n_deltas=0)
+C_MFCC_D2 = replace(C_MFCC, n_deltas=2)
+PRESETS = {"R-SPEC": R_SPEC, "C-SPEC": C_SPEC, "R-FBANK": R_FBANK, "C-FBANK": C_FBANK,
+           "R-MFCC": R_MFCC, "C-MFCC": C_MFCC, "C-MFCC-D2": C_MFCC_D2}
+
+_FAMILY = {SpecParams: "spec", FbankParams: "fbank", MfccParams: "mfcc"}
+
+
+def out_shape(params, n_samples: int) -> tuple[int, int]:
+    """Per-clip feature shape for ``n_samples`` input samples (host only, no GPU needed)."""
+    fam = _FAMILY[type(params)]
+    shp = (C.c_int64 * 2)()
+    cp = params.to_c()
+    _lib.check(getattr(_lib.lib(), f"srfe_{fam}_out_shape")(C.byref(cp), n_samples, C.byref(shp)))
+    return int(shp[0]), int(shp[1])
+
+
+def bytes_per_clip(params, n_samples: int = 16000) -> int:
+    """Algorithmic bytes per clip: fp32 PCM in + fp32 features out."""
+    fam = _FAMILY[type(params)]
+    cp = params.to_c()
+    return _lib.check(getattr(_lib.lib(), f"srfe_{fam}_bytes_per_clip")(C.byref(cp), n_samples))
+
+
+def launch_count() -> int:
+    return int(_lib.lib().srfe_launch_count())
+
+
+# ------------------------------------------------------------------------------------
+# the three custom ops (CUDA only; no autograd formula: features are always computed
+# under torch.no_grad(), model_mfcc_bgru.py:29)
+# ------------------------------------------------------------------------------------
+def _prep(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        raise TypeError(f"PCM must be float32 (dataset.py:117), got {x.dtype}")
+    if x.dim() != 2:
+        raise ValueError("expected a [n_clips, n_samples] tensor")
+    if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) % 2) or x.data_ptr() % 8:
+        x = x.contiguous()
+        if x.data_ptr() % 8:                       # odd-offset view of a larger buffer
+            x = x.clone()
+    return x
+
+
+def _run_device(fam: str, cp, x: torch.Tensor, out: torch.Tensor) -> None:
+    fn = getattr(_lib.lib(), f"srfe_{fam}_f32")
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        stride = x.stride(0) if x.size(0) > 1 else x.size(1)
+        _lib.check(fn(x.data_ptr(), x.size(0), x.size(1), stride, C.byref(cp), out.data_ptr(), stream))
+
+
+@torch.library.custom_op("srfe::spec", mutates_args=(), device_types="cuda")
+def _spec_op(pcm: torch.Tensor, fs: int, nperseg: int, noverlap: int, take_log: bool, eps: float,
+             layout: int) -> torch.Tensor:
+    cp = SpecParamsC(fs, nperseg, noverlap, int(take_log), eps, layout)
+    shp = (C.c_int64 * 2)()
+    _lib.check(_lib.lib().srfe_spec_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
+    out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
+    _run_device("spec", cp, pcm, out)
+    return out
+
+
+@_spec_op.register_fake
+def _(pcm, fs, nperseg, noverlap, take_log, eps, layout):
+    t = (pcm.size(1) - noverlap) // (nperseg - noverlap)
+    f = nperseg // 2 + 1
+    return pcm.new_empty((pcm.size(0), f, t) if layout == LAYOUT_FT else (pcm.size(0), t, f))
+
+
+@torch.library.custom_op("srfe::fbank", mutates_args=(), device_types="cuda")
+def _fbank_op(pcm: torch.Tensor, fs: int, frame_len: int, frame_step: int, nfft: int, preemph: float,
+              nfilt: int) -> torch.Tensor:
+    cp = FbankParamsC(fs, frame_len, frame_step, nfft, preemph, nfilt)
+    shp = (C.c_int64 * 2)()
+    _lib.check(_lib.lib().srfe_fbank_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
+    out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
+    _run_device("fbank", cp, pcm, out)
+    return out
+
+
+@_fbank_op.register_fake
+def _(pcm, fs, frame_len, frame_step, nfft, preemph, nfilt):
+    t = -(-abs(pcm.size(1) - frame_len) // frame_step)
+    return pcm.new_empty((pcm.size(0), t, nfilt))
+
+
+@torch.library.custom_op("srfe::mfcc", mutates_args=(), device_types="cuda")
+def _mfcc_op(pcm: torch.Tensor, sr: int, n_fft: int, win_length: int, hop: int, n_mels: int, fmin: float,
+             fmax: float, n_mfcc: int, n_deltas: int, top_db: float, amin: float, layout: int) -> torch.Tensor:
+    cp = MfccParamsC(sr, n_fft, win_length, hop, n_mels, fmin, fmax, n_mfcc, n_deltas, top_db, amin, layout)
+    shp = (C.c_int64 * 2)()
+    _lib.check(_lib.lib().srfe_mfcc_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
+    out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
+    _run_device("mfcc", cp, pcm, out)
+    return out
+
+
+@_mfcc_op.register_fake
+def _(pcm, sr, n_fft, win_length, hop, n_mels, fmin, fmax, n_mfcc, n_deltas, top_db, amin, layout):
+    t = 1 + pcm.size(1) // hop
+    r = (1 + n_deltas) * n_mfcc
+    return pcm.new_empty((pcm.size(0), r, t) if layout == LAYOUT_FT else (pcm.size(0), t, r))
+
+
+# ------------------------------------------------------------------------------------
+# batched public API
+# ------------------------------------------------------------------------------------
+def _run_host(fam: str, cp, x: torch.Tensor, shape: tuple[int, int], device: Optional[int]) -> torch.Tensor:
+    if not torch.cuda.is_available():
+        raise RuntimeError("srfe: no CUDA device visible and there is no CPU fallback for the feature front end")
+    dev = torch.cuda.current_device() if device is None else device
+    out = torch.empty((x.size(0),) + shape, dtype=torch.float32, pin_memory=x.is_pinned())
+    stride = x.stride(0) if x.size(0) > 1 else x.size(1)
+    fn = getattr(_lib.lib(), f"srfe_{fam}_host_f32")
+    _lib.check(fn(x.data_ptr(), x.size(0), x.size(1), stride, C.byref(cp), out.data_ptr(), dev))
+    return out
+
+
+def _dispatch(fam: str, params, x: torch.Tensor, device: Optional[int]) -> torch.Tensor:
+    single = x.dim() == 1
+    xb = _prep(x.unsqueeze(0) if single else x)
+    if xb.is_cuda:
+        c = params.to_c()
+        if fam == "spec":
+            y = torch.ops.srfe.spec(xb, c.sample_rate, c.nperseg, c.noverlap, bool(c.take_log), c.log_eps, c.layout)
+        elif fam == "fbank":
+            y = torch.ops.srfe.fbank(xb, c.sample_rate, c.frame_len, c.frame_step, c.n_fft, c.preemph, c.nfilt)
+        else:
+            y = torch.ops.srfe.mfcc(xb, c.sample_rate, c.n_fft, c.win_length, c.hop, c.n_mels, c.fmin, c.fmax,
+                                    c.n_mfcc, c.n_deltas, c.top_db, c.amin, c.layout)
+    else:
+        y = _run_host(fam, params.to_c(), xb, out_shape(params, xb.size(1)), device)
+    return y[0] if single else y
+
+
+def spec(x: torch.Tensor, params: SpecParams = R_SPEC, *, layout: Optional[str] = None,
+         device: Optional[int] = None) -> torch.Tensor:
+    """Batched ``compute_spec``: ``x[B, N]`` -> ``[B, nperseg/2+1, T]`` ('ft') or ``[B, T, nperseg/2+1]`` ('tf')."""
+    if layout is not None:
+        params = replace(params, layout=layout)
+    return _dispatch("spec", params, x, device)
+
+
+def fbank(x: torch.Tensor, params: FbankParams = R_FBANK, *, device: Optional[int] = None) -> torch.Tensor:
+    """Batched ``filter_banks``: ``x[B, N]`` -> ``[B, T, nfilt]``."""
+    return _dispatch("fbank", params, x, device)
+
+
+def mfcc(x: torch.Tensor, params: MfccParams = R_MFCC, *, layout: Optional[str] = None,
+         device: Optional[int] = None) -> torch.Tensor:
+    """Batched ``compute_mfcc``: ``x[B, N]`` -> ``[B, (1+n_deltas) n_mfcc, T]`` ('ft') or transposed ('tf')."""
+    if layout is not None:
+        params = replace(params, layout=layout)
+    return _dispatch("mfcc", params, x, device)
+
+
+# ------------------------------------------------------------------------------------
+# reference-named single-clip functions (same signatures / shapes as the reference)
+# ------------------------------------------------------------------------------------
+def compute_spec(sample: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """model_spec_bgru.compute_spec (``transpose=False`` -> [321,49]) or
+    model_spec_cnn.compute_spec (``transpose=True`` -> [49,321])."""
+    return spec(sample, R_SPEC, layout="tf" if transpose else "ft")
+
+
+def filter_banks(sample: torch.Tensor) -> torch.Tensor:
+    """model_fbanks_cnn.filter_banks -> [98,120] (time x features)."""
+    return fbank(sample, R_FBANK)
+
+
+def compute_mfcc(sample: torch.Tensor) -> torch.Tensor:
+    """model_mfcc_bgru.compute_mfcc -> [39,51] (13 static, 13 delta, 13 delta-delta rows)."""
+    return mfcc(sample, R_MFCC)

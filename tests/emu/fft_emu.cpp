@@ -1,0 +1,73 @@
+// fft_emu.cpp -- CPU lane-by-lane emulation of the half-warp FFT pipeline of
+// speechrecognitionproject_b200/csrc/srfe_fft.cuh (TEST INFRASTRUCTURE).
+//
+// The device code separates its phases with warp syncs; here every phase is run
+// for lanes 0..15 in a loop, against a plain array standing in for the shared
+// memory scratch.  Same templates, same index arithmetic, same tables -- so a
+// wrong permutation or twiddle shows up in `pytest -m "not gpu"` instead of
+// costing a GPU round trip.  Not part of the product; never used as a fallback.
+#include <cstring>
+#include <vector>
+
+#include "../../speechrecognitionproject_b200/csrc/srfe_fft.cuh"
+#include "../../speechrecognitionproject_b200/csrc/srfe_tables.h"
+
+using namespace srfe;
+
+template <int NFFT>
+static void run(const float* xw, float* p) {
+    typedef FftGeom<NFFT> G;
+    std::vector<F2> tw1, twu, tw16;
+    fft_twiddles(NFFT, tw1, twu, tw16);
+    FftTables T;
+    T.tw1 = reinterpret_cast<const cpx*>(tw1.data());
+    T.twu = reinterpret_cast<const cpx*>(twu.data());
+    T.tw16 = reinterpret_cast<const cpx*>(tw16.data());
+
+    std::vector<cpx> scratch(G::SCRATCH_CPX);
+    cpx v[16][G::V];
+    // phase 0: lane l takes z[l + 16 j] = (xw[2m], xw[2m+1])
+    for (int l = 0; l < 16; ++l)
+        for (int j = 0; j < G::V; ++j) {
+            const int m = l + 16 * j;
+            v[l][j] = mk(xw[2 * m], xw[2 * m + 1]);
+        }
+    for (int l = 0; l < 16; ++l) fft_phase1<NFFT>(v[l], l, scratch.data(), T);
+    if (NFFT == 512) {
+        for (int l = 0; l < 16; ++l) fft_phase2_512(l, scratch.data(), v[l]);
+        for (int l = 0; l < 16; ++l) fft_store_z_512(l, v[l], scratch.data());
+    } else {
+        for (int l = 0; l < 16; ++l) fft_phase2_640(l, scratch.data(), v[l], T);
+        for (int l = 0; l < 16; ++l) fft_scatter2_640(l, v[l], scratch.data());
+        for (int l = 0; l < 16; ++l) fft_phase3_640(l, scratch.data(), v[l]);
+        for (int l = 0; l < 16; ++l) fft_store_z_640(l, v[l], scratch.data());
+    }
+    for (int l = 0; l < 16; ++l) {
+        float pa[G::M / 32], pb[G::M / 32];
+        const float pmid = fft_untangle<NFFT>(l, scratch.data(), T, pa, pb);
+        for (int r = 0; r < G::M / 32; ++r) {
+            const int k = l + 16 * r;
+            p[k] = 0.25f * pa[r];
+            p[G::M - k] = 0.25f * pb[r];
+        }
+        if (l == 0) p[G::M / 2] = 0.25f * pmid;
+    }
+}
+
+extern "C" int emu_power(int nfft, const float* xw, float* p) {
+    if (nfft == 512) { run<512>(xw, p); return 0; }
+    if (nfft == 640) { run<640>(xw, p); return 0; }
+    return -1;
+}
+
+extern "C" int emu_dft(int n, const float* in_ri, float* out_ri) {
+    cpx v[20];
+    for (int i = 0; i < n; ++i) v[i] = mk(in_ri[2 * i], in_ri[2 * i + 1]);
+    if (n == 4) dft4(v[0], v[1], v[2], v[3]);
+    else if (n == 5) dft5(v[0], v[1], v[2], v[3], v[4]);
+    else if (n == 16) dft16(v);
+    else if (n == 20) dft20(v);
+    else return -1;
+    for (int i = 0; i < n; ++i) { out_ri[2 * i] = v[i].x; out_ri[2 * i + 1] = v[i].y; }
+    return 0;
+}

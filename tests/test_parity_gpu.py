@@ -1,0 +1,240 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs the CPU oracle on seeded inputs.
+
+Reference behaviour being matched (citations into /root/reference):
+compute_spec (models/model_spec_bgru.py:11-17, model_spec_cnn.py:12-18),
+filter_banks (models/model_fbanks_cnn.py:15-66), compute_mfcc
+(models/model_mfcc_bgru.py:11-19).  Tolerances: tests/tolerances.py.
+"""
+from __future__ import annotations
+
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import speechrecognitionproject_b200 as S
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return oracle.synthetic_corpus(24, config_index=1)
+
+
+@pytest.fixture(scope="module")
+def edges():
+    e = oracle.edge_suite()
+    return list(e.keys()), np.stack(list(e.values()))
+
+
+def _gpu(fn, x, p, **kw):
+    y = fn(torch.from_numpy(x).cuda(), p, **kw)
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+# ---------------------------------------------------------------- golden (reference) ----
+def test_golden_spec(srfe_lib, golden):
+    x = golden["x"]
+    got = _gpu(S.spec, x, S.R_SPEC)
+    assert got.shape == golden["spec_ft"].shape == (x.shape[0], 321, 49)
+    H.check_logspec(got, golden["spec_ft"].astype(np.float64), "golden spec ft")
+    got_tf = _gpu(S.spec, x, S.R_SPEC, layout="tf")
+    assert got_tf.shape == (x.shape[0], 49, 321)
+    np.testing.assert_array_equal(got_tf, np.ascontiguousarray(got.transpose(0, 2, 1)))
+    H.check_logspec(got_tf, golden["spec_tf"].astype(np.float64), "golden spec tf")
+
+
+def test_golden_fbank(srfe_lib, golden):
+    x = golden["x"]
+    got = _gpu(S.fbank, x, S.R_FBANK)
+    assert got.shape == golden["fbank"].shape == (x.shape[0], 98, 120)
+    H.check_logmel(got, golden["fbank"].astype(np.float64), "golden fbank")
+
+
+def test_golden_mfcc(srfe_lib, golden):
+    x = golden["x"]
+    got = _gpu(S.mfcc, x, S.R_MFCC)
+    assert got.shape == golden["mfcc"].shape == (x.shape[0], 39, 51)
+    H.check_mfcc(got, golden["mfcc"].astype(np.float64), "golden mfcc")
+
+
+# ---------------------------------------------------------------- presets vs oracle ----
+@pytest.mark.parametrize("name", ["R-SPEC", "C-SPEC"])
+def test_spec_presets(srfe_lib, corpus, name):
+    p = S.PRESETS[name]
+    op = H.to_oracle_params(p)
+    got = _gpu(S.spec, corpus, p)
+    truth = H.oracle_batch(oracle.spec_truth, corpus, op)
+    assert got.shape == truth.shape
+    H.check_logspec(got, truth, name)
+    # raw PSD: relative error on the power spectra themselves
+    praw = replace(p, log=False)
+    got_raw = _gpu(S.spec, corpus, praw)
+    truth_raw = H.oracle_batch(oracle.spec_truth, corpus, H.to_oracle_params(praw))
+    H.check_psd(got_raw, truth_raw, name + " raw")
+    # and against the imported-reference flavour (scipy, single precision)
+    ref = H.oracle_batch(oracle.spec_ref, corpus, op)
+    H.check_logspec(got, ref.astype(np.float64), name + " vs scipy-fp32")
+
+
+@pytest.mark.parametrize("name", ["R-FBANK", "C-FBANK"])
+def test_fbank_presets(srfe_lib, corpus, name):
+    p = S.PRESETS[name]
+    op = H.to_oracle_params(p)
+    got = _gpu(S.fbank, corpus, p)
+    truth = H.oracle_batch(oracle.fbank_truth, corpus, op)
+    assert got.shape == truth.shape
+    stats = H.check_logmel(got, truth, name)
+    assert stats["frac_outside"] < 0.12, stats          # R-FBANK: 10 of 120 filters are structurally empty
+    ref = H.oracle_batch(oracle.fbank_ref, corpus, op)
+    H.check_logmel(got, ref.astype(np.float64), name + " vs reference dtype path")
+
+
+@pytest.mark.parametrize("name", ["R-MFCC", "C-MFCC", "C-MFCC-D2"])
+def test_mfcc_presets(srfe_lib, corpus, name):
+    p = S.PRESETS[name]
+    op = H.to_oracle_params(p)
+    got = _gpu(S.mfcc, corpus, p)
+    truth = H.oracle_batch(oracle.mfcc_truth, corpus, op)
+    assert got.shape == truth.shape
+    H.check_mfcc(got, truth, name)
+    ref = H.oracle_batch(oracle.mfcc_ref, corpus, op)
+    H.check_mfcc(got, ref.astype(np.float64), name + " vs restated librosa dtype path")
+    got_tf = _gpu(S.mfcc, corpus, p, layout="tf")
+    np.testing.assert_array_equal(got_tf, np.ascontiguousarray(got.transpose(0, 2, 1)))
+
+
+# ---------------------------------------------------------------- edge clips -----------
+def test_edge_suite(srfe_lib, edges):
+    names, x = edges
+    got = _gpu(S.mfcc, x, S.R_MFCC)
+    truth = H.oracle_batch(oracle.mfcc_truth, x, oracle.R_MFCC)
+    for i, n in enumerate(names):
+        H.check_mfcc(got[i:i + 1], truth[i:i + 1], f"edge mfcc {n}")
+    got = _gpu(S.fbank, x, S.R_FBANK)
+    truth = H.oracle_batch(oracle.fbank_truth, x, oracle.R_FBANK)
+    for i, n in enumerate(names):
+        H.check_logmel(got[i:i + 1], truth[i:i + 1], f"edge fbank {n}")
+    got = _gpu(S.spec, x, S.R_SPEC)
+    truth = H.oracle_batch(oracle.spec_truth, x, oracle.R_SPEC)
+    for i, n in enumerate(names):
+        H.check_logspec(got[i:i + 1], truth[i:i + 1], f"edge spec {n}")
+
+
+def test_known_answers(srfe_lib):
+    z = torch.zeros(2, 16000, device="cuda")
+    s = S.spec(z).cpu().numpy()
+    np.testing.assert_allclose(s, np.log(np.float32(1e-10)), rtol=0, atol=2e-5)
+    f = S.fbank(z).cpu().numpy()
+    np.testing.assert_allclose(f, 20 * np.log10(np.finfo(float).eps), rtol=0, atol=1e-3)
+    m = S.mfcc(z).cpu().numpy()
+    np.testing.assert_allclose(m[:, 0, :], -100.0 * np.sqrt(128.0), rtol=0, atol=1e-3)
+    assert np.abs(m[:, 1:, :]).max() <= 1e-3
+    # the 10 structurally empty filters of the reference's 120-band bank are constant for ANY input
+    x = torch.from_numpy(oracle.synthetic_corpus(3, 2)).cuda()
+    f = S.fbank(x).cpu().numpy()
+    empty = [0, 2, 4, 7, 9, 11, 14, 17, 21, 25]
+    np.testing.assert_allclose(f[:, :, empty], 20 * np.log10(np.finfo(float).eps), rtol=0, atol=1e-3)
+    # pure tone at a bin centre: PSD peak 2 (A sum(w)/2)^2 / (fs sum(w^2)) at bin 40
+    n = np.arange(16000)
+    tone = (1000.0 * np.sin(2 * np.pi * 1000.0 * n / 16000.0)).astype(np.float32)
+    psd = S.spec(torch.from_numpy(tone).cuda(), replace(S.R_SPEC, log=False)).cpu().numpy()
+    w = oracle.tukey_periodic(640)
+    expect = 2.0 * (1000.0 * w.sum() / 2.0) ** 2 / (16000.0 * (w * w).sum())
+    assert psd.shape == (321, 49) and psd[:, 10].argmax() == 40
+    np.testing.assert_allclose(psd[40], expect, rtol=2e-4)
+
+
+# ---------------------------------------------------------------- interface behaviour ---
+def test_single_clip_signatures(srfe_lib, corpus):
+    s = torch.from_numpy(corpus[0])
+    for dev in ("cpu", "cuda"):
+        x = s.to(dev)
+        assert S.compute_spec(x).shape == (321, 49)
+        assert S.compute_spec(x, transpose=True).shape == (49, 321)
+        assert S.filter_banks(x).shape == (98, 120)
+        m = S.compute_mfcc(x)
+        assert m.shape == (39, 51) and m.dtype == torch.float32 and m.device.type == dev and m.is_contiguous()
+
+
+def test_host_path_matches_device_path(srfe_lib, corpus):
+    x = torch.from_numpy(corpus)
+    for fn, p in ((S.spec, S.R_SPEC), (S.fbank, S.R_FBANK), (S.mfcc, S.R_MFCC), (S.mfcc, S.C_MFCC)):
+        a = fn(x.cuda(), p).cpu()
+        b = fn(x, p)                       # host entry point: H2D -> kernel -> D2H
+        c = fn(x.pin_memory(), p)
+        assert not b.is_cuda and torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_ragged_and_strided_inputs(srfe_lib, corpus):
+    x = torch.from_numpy(corpus).cuda()
+    full = S.mfcc(x)
+    # empty batch
+    assert S.mfcc(x[:0]).shape == (0, 39, 51)
+    assert S.fbank(x[:0]).shape == (0, 98, 120)
+    # batch of one, and every clip independent of its neighbours (bit-exact)
+    for i in (0, 7, 23):
+        assert torch.equal(S.mfcc(x[i:i + 1])[0], full[i])
+    # row-strided view (clip_stride > n_samples), odd-offset view -> copied
+    wide = torch.zeros(x.size(0), 16384, device="cuda")
+    wide[:, :16000] = x
+    assert torch.equal(S.mfcc(wide[:, :16000]), full)
+    shifted = torch.zeros(x.size(0), 16001, device="cuda")
+    shifted[:, 1:] = x
+    assert torch.equal(S.mfcc(shifted[:, 1:]), full)
+    # other clip lengths: frame counts follow the reference formulas
+    for n in (8000, 12345 * 2 // 2 + 1, 16384):
+        xs = x[:3, :n] if n <= 16000 else torch.cat([x[:3], x[:3, : n - 16000]], 1)
+        xs_np = xs.cpu().numpy()
+        if n % 2 == 0:
+            got = S.mfcc(xs).cpu().numpy()
+            H.check_mfcc(got, H.oracle_batch(oracle.mfcc_truth, xs_np, oracle.R_MFCC), f"mfcc n={n}")
+            got = S.spec(xs).cpu().numpy()
+            H.check_logspec(got, H.oracle_batch(oracle.spec_truth, xs_np, oracle.R_SPEC), f"spec n={n}")
+        got = S.fbank(xs).cpu().numpy()
+        H.check_logmel(got, H.oracle_batch(oracle.fbank_truth, xs_np, oracle.R_FBANK), f"fbank n={n}")
+
+
+def test_errors_are_loud(srfe_lib):
+    x = torch.zeros(2, 16000, device="cuda")
+    with pytest.raises(RuntimeError):
+        S.spec(x, S.SpecParams(nperseg=600, noverlap=300))
+    with pytest.raises(RuntimeError):
+        S.mfcc(x, replace(S.R_MFCC, n_mfcc=200))
+    with pytest.raises(TypeError):
+        S.mfcc(x.double())
+    with pytest.raises(RuntimeError):
+        S.mfcc(torch.zeros(1, 200, device="cuda"))
+
+
+def test_deterministic_and_stream_ordered(srfe_lib, corpus):
+    x = torch.from_numpy(corpus).cuda()
+    a = S.fbank(x)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        b = S.fbank(x)
+    st.synchronize()
+    assert torch.equal(a, b)
+
+
+def test_shards_concatenate_bit_exact(srfe_lib, corpus):
+    """Multi-GPU contract: features of a batch == concatenation of its shards."""
+    from speechrecognitionproject_b200.sharding import shard_range
+    x = torch.from_numpy(corpus).cuda()
+    for fn, p in ((S.spec, S.R_SPEC), (S.fbank, S.C_FBANK), (S.mfcc, S.C_MFCC)):
+        whole = fn(x, p)
+        for world in (2, 4, 8):
+            parts = [fn(x[slice(*shard_range(x.size(0), r, world))], p) for r in range(world)]
+            assert torch.equal(torch.cat(parts), whole)
+
+
+def test_launch_counter(srfe_lib, corpus):
+    x = torch.from_numpy(corpus).cuda()
+    n0 = S.launch_count()
+    S.mfcc(x); S.spec(x); S.fbank(x)
+    assert S.launch_count() == n0 + 3
