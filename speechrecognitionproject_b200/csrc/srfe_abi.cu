@@ -187,6 +187,9 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.amin = p.amin;
     e->kp.layout = p.layout;
     e->kp.tile_stride = p.n_mels | 1;                                  // odd: conflict-free column reads
+    double rs0 = 0.0;
+    for (int f = 0; f < p.n_mels; ++f) rs0 += dct[f];
+    e->kp.dct_row0_sum = (float)rs0;                                   // = sqrt(n_mels)
     std::vector<float> dct_t((size_t)p.n_mels * e->kp.n_mfcc_pad, 0.f);
     for (int k = 0; k < p.n_mfcc; ++k)
         for (int f = 0; f < p.n_mels; ++f) dct_t[(size_t)f * e->kp.n_mfcc_pad + k] = (float)dct[(size_t)k * p.n_mels + f];
@@ -196,9 +199,9 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
 // ------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------
-template <int NFFT, int FAM>
-static int launch_t(const KParams& kp, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM>;
+template <int NFFT, int FAM, int JLO, int JHI>
+static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
@@ -209,17 +212,41 @@ static int launch_t(const KParams& kp, int smem_bytes, cudaStream_t st) {
             g_attr_set[tag] = true;
         }
     }
-    srfe_kernel<NFFT, FAM><<<kp.n_clips, kThreads, smem_bytes, st>>>(kp);
+    kern<<<grid, threads, smem_bytes, st>>>(kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "srfe_kernel launch");
     g_launches.fetch_add(1);
     return SRFE_OK;
 }
 
+// Slots per CTA (S, even, <= 16) and clips per CTA so that cpc*T fills whole rounds of S
+// frames: score = round efficiency x a mild preference for more resident warps.
+static void pick_config(int family, int T, int n_clips, int* S_out, int* cpc_out) {
+    double best = -1.0;
+    int bs = kMaxSlots, bc = 1;
+    const int cpc_max = (family == FAM_MFCC) ? 1 : 4;
+    for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
+        if (cpc > 1 && cpc > n_clips) break;
+        for (int S = kMaxSlots; S >= 8; S -= 2) {
+            const long long nf = (long long)cpc * T;
+            const long long rounds = (nf + S - 1) / S;
+            double score = (double)nf / (double)(rounds * S);
+            score *= 0.75 + 0.25 * (double)S / kMaxSlots;
+            score *= 1.0 - 0.005 * (cpc - 1);
+            if (score > best + 1e-9) { best = score; bs = S; bc = cpc; }
+        }
+    }
+    *S_out = bs;
+    *cpc_out = bc;
+}
+
 static int launch(const Entry* e, KParams kp, cudaStream_t st) {
-    const int scratch = kSlots * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
+    int S = kMaxSlots, cpc = 1;
+    pick_config(e->family, kp.T, kp.n_clips, &S, &cpc);
+    kp.cpc = cpc;
+    const int scratch = S * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
     int tile = 0;
-    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT) tile = e->n_bins * kSpecTileStride * 4;
+    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT) tile = 2 * e->n_bins * (S + 1) * 4;   // double-buffered
     if (e->family == FAM_MFCC) {
         tile = kp.T * kp.tile_stride * 4;
         const int TC = kp.T + 1;
@@ -231,15 +258,31 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
     kp.sm_tile = kp.sm_scratch + scratch;
     const int smem = kp.sm_tile + align16(tile);
     if (smem > 200 * 1024) return fail(SRFE_ERR_TOO_LARGE, "clip too long: per-clip tile exceeds shared memory");
-    if (kp.n_clips == 0) return SRFE_OK;
-#define SRFE_DISPATCH(N)                                                       \
-    switch (e->family) {                                                       \
-        case FAM_SPEC: return launch_t<N, FAM_SPEC>(kp, smem, st);             \
-        case FAM_FBANK: return launch_t<N, FAM_FBANK>(kp, smem, st);           \
-        default: return launch_t<N, FAM_MFCC>(kp, smem, st);                   \
+    if (kp.n_clips == 0 || kp.T == 0) return SRFE_OK;
+    const int grid = (kp.n_clips + cpc - 1) / cpc, threads = 16 * S;
+    // window extent in units of 32 samples; known extents get a specialised instantiation
+    const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
+#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(kp, grid, threads, smem, st)
+    if (e->n_fft == 512) {
+        switch (e->family) {
+            case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16);
+            case FAM_FBANK:
+                if (jlo == 0 && jhi <= 13) SRFE_GO(512, FAM_FBANK, 0, 13);
+                SRFE_GO(512, FAM_FBANK, 0, 16);
+            default:
+                if (jlo >= 1 && jhi <= 15) SRFE_GO(512, FAM_MFCC, 1, 15);
+                SRFE_GO(512, FAM_MFCC, 0, 16);
+        }
+    } else {
+        switch (e->family) {
+            case FAM_SPEC: SRFE_GO(640, FAM_SPEC, 0, 20);
+            case FAM_FBANK:
+                if (jlo == 0 && jhi <= 13) SRFE_GO(640, FAM_FBANK, 0, 13);
+                SRFE_GO(640, FAM_FBANK, 0, 20);
+            default: SRFE_GO(640, FAM_MFCC, 0, 20);
+        }
     }
-    if (e->n_fft == 512) { SRFE_DISPATCH(512) } else { SRFE_DISPATCH(640) }
-#undef SRFE_DISPATCH
+#undef SRFE_GO
 }
 
 static int check_buffers(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const void* p,

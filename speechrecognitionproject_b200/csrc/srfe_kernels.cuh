@@ -1,14 +1,20 @@
 // srfe_kernels.cuh -- fused feature kernels for sm_100a.
 //
-// One CTA (256 threads = 16 half-warps) owns one clip.  Each half-warp takes
-// frames t = hw, hw+16, ...:
+// One CTA owns `cpc` consecutive clips (1 for MFCC, 1..4 for SPEC/FBANK) and runs
+// S = blockDim/16 "slots" (half-warps).  Slot s takes the flattened frames
+// f = s, s+S, ... of the CTA's clips; S and cpc are picked on the host so that
+// cpc*T is (nearly) a multiple of S (e.g. T=49: S=14, cpc=2 -> 7 full rounds).
 //
 //   global PCM --LDG.64, coalesced (16 lanes x 8 B = one 128 B line per load; the
-//                2-2.5x frame overlap is served by L1/L2, HBM sees each sample once)
+//                2-2.5x frame overlap is served by L1/L2, HBM sees each sample once);
+//                the NEXT frame of the slot is fetched into registers while the
+//                current one is in its second FFT pass (software pipelining)
 //     -> pre-emphasis (fbank, exact fp32 rounding) -> window (shared table)
-//     -> half-warp FFT (srfe_fft.cuh: registers + one/two shared-memory exchanges)
+//     -> half-warp FFT (srfe_fft.cuh: registers + one/two shared-memory exchanges);
+//        the window extent [32 JLO, 32 JHI) is a template parameter, so the zero
+//        inputs of the 400-in-512 frames are constant-folded out of the first pass
 //     -> untangle -> power
-//     -> SPEC : scale, ln(. + eps)             -> global (TF) or 16-frame tile (FT)
+//     -> SPEC : scale, ln(. + eps)             -> global (TF) or double-buffered tile (FT)
 //        FBANK: sparse triangle sums, 20 log10 -> global [T][nfilt]
 //        MFCC : sparse Slaney sums, 10 log10   -> per-clip dB tile in shared memory
 //   MFCC epilogue (after a CTA barrier): clip max -> top_db clamp -> DCT-II ->
@@ -25,9 +31,8 @@ namespace srfe {
 
 enum Family { FAM_SPEC = 0, FAM_FBANK = 1, FAM_MFCC = 2 };
 
-constexpr int kThreads = 256;          // 8 warps = 16 frame slots per CTA
-constexpr int kSlots = kThreads / 16;
-constexpr int kSpecTileStride = 17;    // FT staging tile: [bins][16 frames + 1 pad]
+constexpr int kMaxThreads = 256;       // <= 8 warps = 16 slots per CTA
+constexpr int kMaxSlots = kMaxThreads / 16;
 
 struct KParams {
     const float* pcm;
@@ -35,7 +40,7 @@ struct KParams {
     long long clip_stride;
     int n_clips, n_samples;
     int T, hop, start0;
-    int w_lo, w_hi;                    // even-aligned non-zero range of the n_fft-long window
+    int cpc;                           // clips per CTA
     const unsigned char* blob;         // tables, copied to shared memory by every CTA
     int blob_bytes;                    // multiple of 16
     int off_win, off_tw1, off_twu, off_tw16, off_fs, off_fc, off_fo, off_fw;
@@ -44,14 +49,15 @@ struct KParams {
     int take_log, layout;
     float preemph;
     int n_mfcc, n_mfcc_pad, n_deltas;
-    float top_db, amin;
+    float top_db, amin, dct_row0_sum;
     const float* dct_t;                // global [n_mels][n_mfcc_pad]
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (floats), odd
+    int w_lo, w_hi;                    // non-zero extent of the window (informational)
 };
 
 // --------------------------------------------------------------------------------
-// frame load: v[j] = window[n] * s(base + n), n = 2 l + 32 j (+1)
+// frame fetch: raw samples for n = 2 l + 32 j (+1), j in [JLO, JHI)
 // --------------------------------------------------------------------------------
 template <int FAM>
 __device__ __forceinline__ float edge_sample(const KParams& p, const float* __restrict__ x, int idx) {
@@ -63,45 +69,57 @@ __device__ __forceinline__ float edge_sample(const KParams& p, const float* __re
     if (FAM == FAM_FBANK) {                                 // zero padding past the clip; e[0] = x[0]
         if (idx >= p.n_samples) return 0.f;
         const float prev = idx > 0 ? __ldg(x + idx - 1) : 0.f;
-        return __fsub_rn(__ldg(x + idx), __fmul_rn(p.preemph, prev));
+        return __fsub_rn(__ldg(x + idx), __fmul_rn(p.preemph, prev));   // model_fbanks_cnn.py:20 (float32)
     }
     return (idx >= 0 && idx < p.n_samples) ? __ldg(x + idx) : 0.f;
 }
 
-template <int NFFT, int FAM>
-__device__ __forceinline__ void load_frame(const KParams& p, const float* __restrict__ x, int base, int l,
-                                           const float* s_win, cpx* v) {
-    typedef FftGeom<NFFT> G;
-    const bool interior = (base + p.w_lo >= 0) && (base + p.w_hi <= p.n_samples);
+template <int FAM, int NJ>
+struct RawFrame {
+    float2 s[NJ];
+    float prev[FAM == FAM_FBANK ? NJ : 1];
+    bool final_;                       // samples already carry the pre-emphasis (edge path)
+};
+
+template <int FAM, int JLO, int JHI>
+__device__ __forceinline__ void fetch_frame(const KParams& p, const float* __restrict__ x, int base, int l,
+                                            RawFrame<FAM, JHI - JLO>& r) {
+    const bool interior = (base + 32 * JLO >= 0) && (base + 32 * JHI <= p.n_samples);
+    r.final_ = !interior;
     if (interior) {
+        const float* xs = x + base + 2 * l;
 #pragma unroll
-        for (int j = 0; j < G::V; ++j) {
-            const int n = 2 * l + 32 * j;
-            if (n >= p.w_lo && n < p.w_hi) {
-                const float2 w = *reinterpret_cast<const float2*>(s_win + n);
-                const float2 s = __ldg(reinterpret_cast<const float2*>(x + base + n));
-                float s0 = s.x, s1 = s.y;
-                if (FAM == FAM_FBANK) {                     // model_fbanks_cnn.py:20, float32, no FMA contraction
-                    const int i0 = base + n;
-                    const float prev = i0 > 0 ? __ldg(x + i0 - 1) : 0.f;
-                    s0 = __fsub_rn(s.x, __fmul_rn(p.preemph, prev));
-                    s1 = __fsub_rn(s.y, __fmul_rn(p.preemph, s.x));
-                }
-                v[j] = mk(w.x * s0, w.y * s1);
-            } else {
-                v[j] = mk(0.f, 0.f);
-            }
+        for (int j = JLO; j < JHI; ++j) {
+            r.s[j - JLO] = __ldg(reinterpret_cast<const float2*>(xs + 32 * j));
+            if (FAM == FAM_FBANK) r.prev[j - JLO] = (base + 2 * l + 32 * j > 0) ? __ldg(xs + 32 * j - 1) : 0.f;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < G::V; ++j) {
-            const int n = 2 * l + 32 * j;
-            if (n >= p.w_lo && n < p.w_hi) {
-                const float2 w = *reinterpret_cast<const float2*>(s_win + n);
-                v[j] = mk(w.x * edge_sample<FAM>(p, x, base + n), w.y * edge_sample<FAM>(p, x, base + n + 1));
-            } else {
-                v[j] = mk(0.f, 0.f);
+        for (int j = JLO; j < JHI; ++j) {
+            const int i = base + 2 * l + 32 * j;
+            r.s[j - JLO] = make_float2(edge_sample<FAM>(p, x, i), edge_sample<FAM>(p, x, i + 1));
+            if (FAM == FAM_FBANK) r.prev[j - JLO] = 0.f;
+        }
+    }
+}
+
+// v[j] = window[n] * s[n]; zero outside [JLO, JHI) (compile-time, folds into the DFT)
+template <int NFFT, int FAM, int JLO, int JHI>
+__device__ __forceinline__ void window_frame(const KParams& p, const RawFrame<FAM, JHI - JLO>& r, int l,
+                                             const float* s_win, cpx* v) {
+    typedef FftGeom<NFFT> G;
+#pragma unroll
+    for (int j = 0; j < G::V; ++j) {
+        if (j >= JLO && j < JHI) {
+            const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * l + 32 * j);
+            float s0 = r.s[j - JLO].x, s1 = r.s[j - JLO].y;
+            if (FAM == FAM_FBANK && !r.final_) {            // float32, no FMA contraction
+                s1 = __fsub_rn(s1, __fmul_rn(p.preemph, s0));
+                s0 = __fsub_rn(s0, __fmul_rn(p.preemph, r.prev[j - JLO]));
             }
+            v[j] = mk(w.x * s0, w.y * s1);
+        } else {
+            v[j] = mk(0.f, 0.f);
         }
     }
 }
@@ -109,16 +127,18 @@ __device__ __forceinline__ void load_frame(const KParams& p, const float* __rest
 // --------------------------------------------------------------------------------
 // the fused kernel
 // --------------------------------------------------------------------------------
-template <int NFFT, int FAM>
-__global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
+template <int NFFT, int FAM, int JLO, int JHI>
+__global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
     typedef FftGeom<NFFT> G;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int S = nthr >> 4;
 
     {   // tables -> shared memory (L2-resident after the first CTA)
         const int4* src = reinterpret_cast<const int4*>(p.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
-        for (int i = tid; i < p.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < p.blob_bytes / 16; i += nthr) dst[i] = __ldg(src + i);
     }
     const float* s_win = reinterpret_cast<const float*>(smem + p.off_win);
     FftTables T;
@@ -136,18 +156,34 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
     const int hw = tid >> 4, l = tid & 15;
     const unsigned hm = 0xFFFFu << (16 * (hw & 1));
     cpx* xb = scratch_all + hw * G::SCRATCH_CPX;
-    const int clip = blockIdx.x;
-    const float* __restrict__ x = p.pcm + (long long)clip * p.clip_stride;
+    const int clip0 = blockIdx.x * p.cpc;
+    const int ncl = min(p.cpc, p.n_clips - clip0);
+    const int nf = ncl * p.T;                               // flattened frames of this CTA
     constexpr int F = G::M + 1;
+    const int TS = S + 1;                                   // FT tile row stride (odd)
     float run_max = -CUDART_INF_F;
 
-    const int iters = (p.T + kSlots - 1) / kSlots;
-    for (int it = 0; it < iters; ++it) {
-        const int t = it * kSlots + hw;
-        if (t < p.T) {
+    RawFrame<FAM, JHI - JLO> raw;
+    int c_cur = 0, t_cur = hw;                              // (clip, frame) of flattened index f
+    while (t_cur >= p.T && c_cur < ncl) { t_cur -= p.T; ++c_cur; }
+    if (hw < nf)
+        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + c_cur) * p.clip_stride, p.start0 + t_cur * p.hop, l, raw);
+
+    const int rounds = (nf + S - 1) / S;
+    for (int it = 0; it < rounds; ++it) {
+        const int f = it * S + hw;
+        if (f < nf) {
+            const int c = c_cur, t = t_cur;
             cpx v[G::V];
-            load_frame<NFFT, FAM>(p, x, p.start0 + t * p.hop, l, s_win, v);
+            window_frame<NFFT, FAM, JLO, JHI>(p, raw, l, s_win, v);
             fft_phase1<NFFT>(v, l, xb, T);
+            {   // prefetch the slot's next frame while this one goes through the exchange passes
+                t_cur += S;
+                while (t_cur >= p.T && c_cur < ncl) { t_cur -= p.T; ++c_cur; }
+                if (f + S < nf)
+                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + c_cur) * p.clip_stride,
+                                               p.start0 + t_cur * p.hop, l, raw);
+            }
             __syncwarp(hm);
             if (NFFT == 512) {
                 fft_phase2_512(l, xb, v);
@@ -169,38 +205,28 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
             if (FAM == FAM_SPEC) {
                 // density scaling, one-sided doubling (not DC / Nyquist), optional ln(. + eps)
                 const float s2 = 2.f * p.scale;
+                float* dst;
+                int kstride;
                 if (p.layout == SRFE_LAYOUT_TF) {
-                    float* row = p.out + ((long long)clip * p.T + t) * F;
-#pragma unroll
-                    for (int r = 0; r < G::M / 32; ++r) {
-                        const int k = l + 16 * r;
-                        float a = pa[r] * (k == 0 ? p.scale : s2);
-                        float b = pb[r] * (k == 0 ? p.scale : s2);
-                        if (p.take_log) { a = __logf(a + p.log_eps); b = __logf(b + p.log_eps); }
-                        row[k] = a;
-                        row[G::M - k] = b;
-                    }
-                    if (l == 0) {
-                        float c = pmid * s2;
-                        if (p.take_log) c = __logf(c + p.log_eps);
-                        row[G::M / 2] = c;
-                    }
+                    dst = p.out + ((long long)(clip0 + c) * p.T + t) * F;
+                    kstride = 1;
                 } else {
-                    float* col = tile + (t & (kSlots - 1));
+                    dst = tile + (it & 1) * (F * TS) + hw;
+                    kstride = TS;
+                }
 #pragma unroll
-                    for (int r = 0; r < G::M / 32; ++r) {
-                        const int k = l + 16 * r;
-                        float a = pa[r] * (k == 0 ? p.scale : s2);
-                        float b = pb[r] * (k == 0 ? p.scale : s2);
-                        if (p.take_log) { a = __logf(a + p.log_eps); b = __logf(b + p.log_eps); }
-                        col[k * kSpecTileStride] = a;
-                        col[(G::M - k) * kSpecTileStride] = b;
-                    }
-                    if (l == 0) {
-                        float c = pmid * s2;
-                        if (p.take_log) c = __logf(c + p.log_eps);
-                        col[(G::M / 2) * kSpecTileStride] = c;
-                    }
+                for (int r = 0; r < G::M / 32; ++r) {
+                    const int k = l + 16 * r;
+                    float a = pa[r] * ((r == 0 && l == 0) ? p.scale : s2);
+                    float b = pb[r] * ((r == 0 && l == 0) ? p.scale : s2);
+                    if (p.take_log) { a = __logf(a + p.log_eps); b = __logf(b + p.log_eps); }
+                    dst[k * kstride] = a;
+                    dst[(G::M - k) * kstride] = b;
+                }
+                if (l == 0) {
+                    float cc = pmid * s2;
+                    if (p.take_log) cc = __logf(cc + p.log_eps);
+                    dst[(G::M / 2) * kstride] = cc;
                 }
             } else {
                 // power -> shared (aliases the FFT scratch), then sparse triangular sums
@@ -214,16 +240,20 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
                 }
                 if (l == 0) pbuf[G::M / 2] = pmid;
                 __syncwarp(hm);
+                float* orow = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + c) * p.T + t) * p.n_filt
+                                                 : tile + t * p.tile_stride;
                 for (int m = l; m < p.n_filt; m += 16) {
-                    const int s = f_start[m], c = f_count[m], o = f_off[m];
+                    const int s = f_start[m], cn = f_count[m];
+                    const float* wq = f_w + f_off[m];
+                    const float* pq = pbuf + s;
                     float acc = 0.f;
-                    for (int q = 0; q < c; ++q) acc = fmaf(f_w[o + q], pbuf[s + q], acc);
+                    for (int q = 0; q < cn; ++q) acc = fmaf(wq[q], pq[q], acc);
                     if (FAM == FAM_FBANK) {
                         if (acc == 0.f) acc = 2.220446049250313e-16f;              // model_fbanks_cnn.py:61
-                        p.out[((long long)clip * p.T + t) * p.n_filt + m] = 6.020599913279624f * __log2f(acc);   // 20 log10
+                        orow[m] = 6.020599913279624f * __log2f(acc);               // 20 log10
                     } else {
                         const float db = 3.010299956639812f * __log2f(fmaxf(acc, p.amin));   // 10 log10
-                        tile[t * p.tile_stride + m] = db;
+                        orow[m] = db;
                         run_max = fmaxf(run_max, db);
                     }
                 }
@@ -231,46 +261,50 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
             }
         }
         if (FAM == FAM_SPEC && p.layout == SRFE_LAYOUT_FT) {
+            // 16*S threads: thread -> (slot = tid % S, k = tid / S + 16 i); one barrier per round
             __syncthreads();
-            const int t0 = it * kSlots;
-            const int nt = min(kSlots, p.T - t0);
-            float* oc = p.out + (long long)clip * F * p.T + t0;
-            for (int idx = tid; idx < F * kSlots; idx += kThreads) {
-                const int k = idx >> 4, tt = idx & 15;
-                if (tt < nt) oc[(long long)k * p.T + tt] = tile[k * kSpecTileStride + tt];
+            const int slot = tid % S;
+            const int fs = it * S + slot;
+            if (fs < nf) {
+                const int c = fs / p.T, t = fs - c * p.T;
+                const float* src = tile + (it & 1) * (F * TS) + slot;
+                float* oc = p.out + (long long)(clip0 + c) * F * p.T + t;
+                for (int k = tid / S; k < F; k += 16) oc[(long long)k * p.T] = src[k * TS];
             }
-            __syncthreads();
         }
     }
 
     if (FAM == FAM_MFCC) {
-        __shared__ float s_red[kThreads / 32];
+        __shared__ float s_red[kMaxThreads / 32];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
         if ((tid & 31) == 0) s_red[tid >> 5] = run_max;
         __syncthreads();
         float gmax = s_red[0];
-#pragma unroll
-        for (int i = 1; i < kThreads / 32; ++i) gmax = fmaxf(gmax, s_red[i]);
+        for (int i = 1; i < (nthr >> 5); ++i) gmax = fmaxf(gmax, s_red[i]);
         const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
+        // DCT-II on values re-centred around g0 (the clamp bounds them to [g0 - top_db/2, g0 + top_db/2]):
+        //   C[k] = sum_f D[k][f] (dB[f] - g0) + g0 * sum_f D[k][f],  sum_f D[k][f] = sqrt(n_mels) [k == 0]
+        // keeps the fp32 accumulation error of c0 (~1e3) an order of magnitude below the 1e-3 tolerance.
+        const float g0 = p.top_db >= 0.f ? gmax - 0.5f * p.top_db : gmax;
 
-        // DCT-II: C[k][t] = sum_f D[k][f] max(dB[t][f], thr); 4 coefficients per thread
         const int TC = p.T + 1;
         float* ctile = reinterpret_cast<float*>(scratch_all);
         const int kq_n = p.n_mfcc_pad / 4;
-        for (int task = tid; task < p.T * kq_n; task += kThreads) {
+        for (int task = tid; task < p.T * kq_n; task += nthr) {
             const int t = task % p.T, kq = task / p.T;
             const float* row = tile + t * p.tile_stride;
             const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int f = 0; f < p.n_filt; ++f) {
-                const float d = fmaxf(row[f], thr);
+                const float d = fmaxf(row[f], thr) - g0;
                 const float4 w = __ldg(dcol + f * kq_n);
                 acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
                 acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
             }
             const int k0 = 4 * kq;
+            if (k0 == 0) acc.x = fmaf(g0, p.dct_row0_sum, acc.x);
             ctile[(k0 + 0) * TC + t] = acc.x;
             if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
             if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
@@ -281,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
         for (int d = 1; d <= p.n_deltas; ++d) {
             const float* src = ctile + (d - 1) * p.n_mfcc * TC;
             float* dst = ctile + d * p.n_mfcc * TC;
-            for (int idx = tid; idx < p.n_mfcc * p.T; idx += kThreads) {
+            for (int idx = tid; idx < p.n_mfcc * p.T; idx += nthr) {
                 const int k = idx / p.T, t = idx % p.T;
                 const float* s = src + k * TC;
                 float g;
@@ -293,11 +327,11 @@ __global__ void __launch_bounds__(kThreads, 2) srfe_kernel(const KParams p) {
             __syncthreads();
         }
         const int R = (1 + p.n_deltas) * p.n_mfcc;
-        float* oc = p.out + (long long)clip * R * p.T;
+        float* oc = p.out + (long long)clip0 * R * p.T;
         if (p.layout == SRFE_LAYOUT_FT) {
-            for (int idx = tid; idx < R * p.T; idx += kThreads) oc[idx] = ctile[(idx / p.T) * TC + idx % p.T];
+            for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx / p.T) * TC + idx % p.T];
         } else {
-            for (int idx = tid; idx < R * p.T; idx += kThreads) oc[idx] = ctile[(idx % R) * TC + idx / R];
+            for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx % R) * TC + idx / R];
         }
     }
 }
