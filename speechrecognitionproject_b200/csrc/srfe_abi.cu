@@ -37,6 +37,7 @@ struct Entry {
     int blob_smem = 0;
     void* d_blob = nullptr;
     void* d_dct = nullptr;
+    void* d_dct_kf = nullptr;
     int n_bins = 0;
 };
 
@@ -74,7 +75,13 @@ static void window_range(const std::vector<double>& w, int& lo, int& hi) {
     hi = (b + 2) & ~1;                                   // exclusive, rounded up to even
 }
 
-static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct_t) {
+static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct_t,
+                  const std::vector<float>& dct_kf = std::vector<float>()) {
+    if (!dct_kf.empty()) {
+        SRFE_CUDA(cudaMalloc(&e->d_dct_kf, dct_kf.size() * sizeof(float)));
+        SRFE_CUDA(cudaMemcpy(e->d_dct_kf, dct_kf.data(), dct_kf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        e->kp.dct_kf = (const float*)e->d_dct_kf;
+    }
     SRFE_CUDA(cudaMalloc(&e->d_blob, bb.data.size()));
     SRFE_CUDA(cudaMemcpy(e->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
     if (!dct_t.empty()) {
@@ -100,9 +107,10 @@ static void add_fft_tables(BlobBuilder& bb, KParams& kp, int n_fft, const std::v
 }
 
 static void add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb) {
-    kp.off_fs = bb.add(sb.start.data(), sb.start.size() * 4);
-    kp.off_fc = bb.add(sb.count.data(), sb.count.size() * 4);
-    kp.off_fo = bb.add(sb.offset.data(), sb.offset.size() * 4);
+    std::vector<int32_t> meta(sb.start.size());
+    for (size_t i = 0; i < meta.size(); ++i)                         // start | count << 10 | offset << 18
+        meta[i] = (sb.start[i] & 0x3ff) | ((sb.count[i] & 0xff) << 10) | (sb.offset[i] << 18);
+    kp.off_fm = bb.add(meta.data(), meta.size() * 4);
     kp.off_fw = bb.add(sb.weight.data(), sb.weight.size() * 4);
     kp.n_filt = (int)sb.start.size();
 }
@@ -186,14 +194,21 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.top_db = p.top_db;
     e->kp.amin = p.amin;
     e->kp.layout = p.layout;
-    e->kp.tile_stride = p.n_mels | 1;                                  // odd: conflict-free column reads
+    e->kp.use_mma = (p.n_mels % 8 == 0) ? 1 : 0;
+    e->kp.nt8 = (p.n_mfcc + 7) / 8;
+    // tensor-core path: stride = 4 (mod 32) makes the mma fragment loads conflict-free;
+    // CUDA-core path: odd stride for conflict-free column reads
+    e->kp.tile_stride = e->kp.use_mma ? p.n_mels + 4 : (p.n_mels | 1);
     double rs0 = 0.0;
     for (int f = 0; f < p.n_mels; ++f) rs0 += dct[f];
     e->kp.dct_row0_sum = (float)rs0;                                   // = sqrt(n_mels)
     std::vector<float> dct_t((size_t)p.n_mels * e->kp.n_mfcc_pad, 0.f);
     for (int k = 0; k < p.n_mfcc; ++k)
         for (int f = 0; f < p.n_mels; ++f) dct_t[(size_t)f * e->kp.n_mfcc_pad + k] = (float)dct[(size_t)k * p.n_mels + f];
-    return upload(e, bb, dct_t);
+    std::vector<float> dct_kf((size_t)e->kp.nt8 * 8 * p.n_mels, 0.f);
+    for (int k = 0; k < p.n_mfcc; ++k)
+        for (int f = 0; f < p.n_mels; ++f) dct_kf[(size_t)k * p.n_mels + f] = (float)dct[(size_t)k * p.n_mels + f];
+    return upload(e, bb, dct_t, dct_kf);
 }
 
 // ------------------------------------------------------------------------------
@@ -244,13 +259,17 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
     int S = kMaxSlots, cpc = 1;
     pick_config(e->family, kp.T, kp.n_clips, &S, &cpc);
     kp.cpc = cpc;
-    const int scratch = S * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
+    int scratch = S * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
     int tile = 0;
     if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT) tile = 2 * e->n_bins * (S + 1) * 4;   // double-buffered
     if (e->family == FAM_MFCC) {
-        tile = kp.T * kp.tile_stride * 4;
+        tile = kp.T * kp.tile_stride * 4 + kp.T * 4;                 // dB tile + per-frame means
         const int TC = kp.T + 1;
-        if (kp.n_mfcc * TC * 4 > scratch || (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile))
+        // epilogue reuses the FFT scratch: [DCT table (tensor-core path)][static coefficients] must not
+        // reach into the dB tile; the delta rows may (the tile is dead by then)
+        const int dtab = kp.use_mma ? kp.nt8 * 8 * (kp.n_filt + 4) * 4 : 0;
+        if (dtab + kp.n_mfcc * TC * 4 > scratch) scratch = align16(dtab + kp.n_mfcc * TC * 4);
+        if (dtab + (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile))
             return fail(SRFE_ERR_TOO_LARGE, "mfcc: coefficient tile does not fit the per-clip shared memory budget");
         if (kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
     }

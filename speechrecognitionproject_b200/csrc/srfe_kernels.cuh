@@ -43,14 +43,16 @@ struct KParams {
     int cpc;                           // clips per CTA
     const unsigned char* blob;         // tables, copied to shared memory by every CTA
     int blob_bytes;                    // multiple of 16
-    int off_win, off_tw1, off_twu, off_tw16, off_fs, off_fc, off_fo, off_fw;
+    int off_win, off_tw1, off_twu, off_tw16, off_fm, off_fw;   // fm: packed (start | count<<10 | offset<<18)
     int n_filt;
     float scale, log_eps;
     int take_log, layout;
     float preemph;
     int n_mfcc, n_mfcc_pad, n_deltas;
     float top_db, amin, dct_row0_sum;
-    const float* dct_t;                // global [n_mels][n_mfcc_pad]
+    const float* dct_t;                // global [n_mels][n_mfcc_pad]   (CUDA-core DCT path)
+    const float* dct_kf;               // global [nt8*8][n_mels], zero-padded rows (tensor-core DCT path)
+    int use_mma, nt8;                  // DCT on mma.sync 3xTF32 when n_mels % 8 == 0; nt8 = ceil(n_mfcc / 8)
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (floats), odd
     int w_lo, w_hi;                    // non-zero extent of the window (informational)
@@ -125,6 +127,20 @@ __device__ __forceinline__ void window_frame(const KParams& p, const RawFrame<FA
 }
 
 // --------------------------------------------------------------------------------
+// 3xTF32 tensor-core helper for the DCT epilogue (fp32-grade accuracy: the dropped
+// lo*lo term is ~2^-22 relative)
+// --------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;         // round to nearest tf32: lo is signed, |lo| <= 2^-12 |x|
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// --------------------------------------------------------------------------------
 // the fused kernel
 // --------------------------------------------------------------------------------
 template <int NFFT, int FAM, int JLO, int JHI>
@@ -145,12 +161,11 @@ __global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
     T.tw1 = reinterpret_cast<const cpx*>(smem + p.off_tw1);
     T.twu = reinterpret_cast<const cpx*>(smem + p.off_twu);
     T.tw16 = reinterpret_cast<const cpx*>(smem + p.off_tw16);
-    const int* f_start = reinterpret_cast<const int*>(smem + p.off_fs);
-    const int* f_count = reinterpret_cast<const int*>(smem + p.off_fc);
-    const int* f_off = reinterpret_cast<const int*>(smem + p.off_fo);
+    const int* f_meta = reinterpret_cast<const int*>(smem + p.off_fm);
     const float* f_w = reinterpret_cast<const float*>(smem + p.off_fw);
     cpx* scratch_all = reinterpret_cast<cpx*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
+    float* fmean = tile + p.T * p.tile_stride;              // MFCC only: [T] frame means, right after the dB tile
     __syncthreads();
 
     const int hw = tid >> 4, l = tid & 15;
@@ -242,10 +257,12 @@ __global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
                 __syncwarp(hm);
                 float* orow = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + c) * p.T + t) * p.n_filt
                                                  : tile + t * p.tile_stride;
+                float fsum = 0.f;
                 for (int m = l; m < p.n_filt; m += 16) {
-                    const int s = f_start[m], cn = f_count[m];
-                    const float* wq = f_w + f_off[m];
-                    const float* pq = pbuf + s;
+                    const int meta = f_meta[m];
+                    const int cn = (meta >> 10) & 0xff;
+                    const float* wq = f_w + (meta >> 18);
+                    const float* pq = pbuf + (meta & 0x3ff);
                     float acc = 0.f;
                     for (int q = 0; q < cn; ++q) acc = fmaf(wq[q], pq[q], acc);
                     if (FAM == FAM_FBANK) {
@@ -255,7 +272,13 @@ __global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
                         const float db = 3.010299956639812f * __log2f(fmaxf(acc, p.amin));   // 10 log10
                         orow[m] = db;
                         run_max = fmaxf(run_max, db);
+                        fsum += db;
                     }
+                }
+                if (FAM == FAM_MFCC) {                       // per-frame mean dB: centre of the DCT accumulation
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) fsum += __shfl_xor_sync(hm, fsum, o);
+                    if (l == 0) fmean[t] = fsum / (float)p.n_filt;
                 }
                 __syncwarp(hm);
             }
@@ -283,32 +306,93 @@ __global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
         float gmax = s_red[0];
         for (int i = 1; i < (nthr >> 5); ++i) gmax = fmaxf(gmax, s_red[i]);
         const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
-        // DCT-II on values re-centred around g0 (the clamp bounds them to [g0 - top_db/2, g0 + top_db/2]):
-        //   C[k] = sum_f D[k][f] (dB[f] - g0) + g0 * sum_f D[k][f],  sum_f D[k][f] = sqrt(n_mels) [k == 0]
-        // keeps the fp32 accumulation error of c0 (~1e3) an order of magnitude below the 1e-3 tolerance.
-        const float g0 = p.top_db >= 0.f ? gmax - 0.5f * p.top_db : gmax;
-
+        // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
+        //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
+        // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
+        // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
         const int TC = p.T + 1;
-        float* ctile = reinterpret_cast<float*>(scratch_all);
-        const int kq_n = p.n_mfcc_pad / 4;
-        for (int task = tid; task < p.T * kq_n; task += nthr) {
-            const int t = task % p.T, kq = task / p.T;
-            const float* row = tile + t * p.tile_stride;
-            const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int f = 0; f < p.n_filt; ++f) {
-                const float d = fmaxf(row[f], thr) - g0;
-                const float4 w = __ldg(dcol + f * kq_n);
-                acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
-                acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+        float* ctile;
+        if (p.use_mma) {
+            // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels
+            float* dtab = reinterpret_cast<float*>(scratch_all);          // [nt8*8][DS], aliases the FFT scratch
+            const int DS = p.n_filt + 4;
+            ctile = dtab + p.nt8 * 8 * DS;
+            const int q4 = p.n_filt >> 2;
+            for (int idx = tid; idx < p.nt8 * 8 * q4; idx += nthr) {
+                const int row = idx / q4, c4 = idx - row * q4;
+                *reinterpret_cast<float4*>(dtab + row * DS + 4 * c4) =
+                    __ldg(reinterpret_cast<const float4*>(p.dct_kf + row * p.n_filt) + c4);
             }
-            const int k0 = 4 * kq;
-            if (k0 == 0) acc.x = fmaf(g0, p.dct_row0_sum, acc.x);
-            ctile[(k0 + 0) * TC + t] = acc.x;
-            if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
-            if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
-            if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
+            __syncthreads();
+            const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+            const int mtiles = (p.T + 15) >> 4;
+            for (int mt = warp; mt < mtiles; mt += (nthr >> 5)) {
+                float acc[8][4];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+                const int t0 = mt * 16;
+                const int tra = min(t0 + g, p.T - 1), trb = min(t0 + g + 8, p.T - 1);
+                const float* ra = tile + tra * p.tile_stride + q;
+                const float* rb = tile + trb * p.tile_stride + q;
+                const float ca = fmaxf(fmean[tra], thr), cb = fmaxf(fmean[trb], thr);
+                for (int ks = 0; ks < (p.n_filt >> 3); ++ks) {
+                    uint32_t ah[4], al[4];
+                    split_tf32(fmaxf(ra[8 * ks], thr) - ca, ah[0], al[0]);
+                    split_tf32(fmaxf(rb[8 * ks], thr) - cb, ah[1], al[1]);
+                    split_tf32(fmaxf(ra[8 * ks + 4], thr) - ca, ah[2], al[2]);
+                    split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        if (nt < p.nt8) {
+                            const float* dr = dtab + (nt * 8 + g) * DS + 8 * ks + q;
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(dr[0], bh0, bl0);
+                            split_tf32(dr[4], bh1, bl1);
+                            mma_tf32(acc[nt], al, bh0, bh1);
+                            mma_tf32(acc[nt], ah, bl0, bl1);
+                            mma_tf32(acc[nt], ah, bh0, bh1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    if (nt < p.nt8) {
+                        const int k = nt * 8 + 2 * q, ta = t0 + g, tb = t0 + g + 8;
+                        if (k == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
+                        if (k < p.n_mfcc) {
+                            if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
+                            if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
+                        }
+                        if (k + 1 < p.n_mfcc) {
+                            if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
+                            if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
+                        }
+                    }
+                }
+            }
+        } else {
+            ctile = reinterpret_cast<float*>(scratch_all);
+            const int kq_n = p.n_mfcc_pad / 4;
+            for (int task = tid; task < p.T * kq_n; task += nthr) {
+                const int t = task % p.T, kq = task / p.T;
+                const float* row = tile + t * p.tile_stride;
+                const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float ct = fmaxf(fmean[t], thr);
+#pragma unroll 4
+                for (int f = 0; f < p.n_filt; ++f) {
+                    const float d = fmaxf(row[f], thr) - ct;
+                    const float4 w = __ldg(dcol + f * kq_n);
+                    acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
+                    acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+                }
+                const int k0 = 4 * kq;
+                if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
+                ctile[(k0 + 0) * TC + t] = acc.x;
+                if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
+                if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
+                if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
+            }
         }
         __syncthreads();
         // np.gradient along time (unit spacing, edge_order 1), applied n_deltas times
