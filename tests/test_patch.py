@@ -1,0 +1,163 @@
+"""patch_model: the re-plumbed Network.forward (one batched feature call, PCM moved instead of
+features) gives the same logits as the reference's own per-clip CPU loop.
+
+CPU tests drive the patched forward with oracle features (feature_fn hook) so the handoff logic
+is checked without a GPU; when /root/reference is mounted (build container only) the UNMODIFIED
+reference model modules are imported and compared, otherwise structural stand-ins with the same
+attribute names are used.  The GPU test runs the stand-ins with the real kernels."""
+from __future__ import annotations
+
+import importlib.util
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import oracle
+from oracle import librosa_shim
+from speechrecognitionproject_b200 import patch
+
+REF = "/root/reference/models"
+
+
+def _oracle_fn(kind):
+    def f(x):
+        xn = x.detach().cpu().numpy()
+        if kind in ("mfcc_bgru", "mfrn_bgru"):
+            y = np.stack([oracle.mfcc_ref(c).T for c in xn])
+        elif kind in ("spec_bgru", "spec_cnn"):
+            y = np.stack([oracle.spec_ref(c).T for c in xn])
+        else:
+            y = np.stack([oracle.fbank_ref(c) for c in xn])
+        return torch.from_numpy(np.ascontiguousarray(y))
+    return f
+
+
+def _load_ref(name):
+    librosa_shim.install()
+    spec = importlib.util.spec_from_file_location(f"ref_{name}", os.path.join(REF, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("name,kind", [("model_mfcc_bgru", "mfcc_bgru"), ("model_spec_bgru", "spec_bgru"),
+                                       ("model_spec_cnn", "spec_cnn"), ("model_fbanks_cnn", "fbanks_cnn"),
+                                       ("model_mfrn_bgru", "mfrn_bgru")])
+@pytest.mark.filterwarnings("ignore")
+def test_patched_forward_equals_reference_forward(name, kind):
+    mod = _load_ref(name)
+    assert patch.detect_kind(mod) == kind
+    torch.manual_seed(0)
+    kw = {} if "cnn" in kind else {"num_features": 16, "num_layers": 1}
+    net = mod.Network(**kw).eval()
+    keys = list(net.state_dict().keys())
+    x = torch.from_numpy(oracle.synthetic_corpus(3, config_index=6))
+    with torch.no_grad():
+        want = net(x)                                  # reference: per-clip CPU loop
+    patch.patch_model(mod, feature_fn=_oracle_fn(kind))
+    try:
+        with torch.no_grad():
+            got = net(x)                               # one batched feature call
+        assert list(net.state_dict().keys()) == keys   # layers / checkpoint keys untouched
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    finally:
+        patch.unpatch_model(mod)
+    with torch.no_grad():
+        torch.testing.assert_close(net(x), want)       # unpatch restores the original
+
+
+# ---- structural stand-ins (same attribute names / loop shape as the reference modules) -------
+def _standin_mfcc_bgru():
+    m = types.ModuleType("standin_mfcc_bgru")
+
+    def compute_mfcc(sample):
+        return torch.from_numpy(oracle.mfcc_ref(sample.numpy()))
+
+    class Network(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gru = nn.GRU(39, hidden_size=8, num_layers=1, bidirectional=True, batch_first=True)
+            self.fc = nn.Linear(16, 12)
+
+        def forward(self, x):
+            with torch.no_grad():
+                inx = torch.ones(x.size(0), 39, 51)
+                for i in range(x.size(0)):
+                    inx[i] = m.compute_mfcc(x[i])
+            inx = inx.to(next(self.parameters()).device).transpose(1, 2)
+            inx, _ = self.gru(inx)
+            return self.fc(inx[:, -1, :])
+
+    m.compute_mfcc, m.Network = compute_mfcc, Network
+    return m
+
+
+def _standin_fbanks_cnn():
+    m = types.ModuleType("standin_fbanks_cnn")
+
+    def filter_banks(sample):
+        return torch.from_numpy(oracle.fbank_ref(sample.numpy()))
+
+    class Network(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(1, 4, kernel_size=(7, 3), padding=(3, 1))
+            self.maxpool1 = nn.MaxPool2d((1, 3))
+            self.conv2 = nn.Conv2d(4, 4, (1, 7), padding=(0, 3))
+            self.maxpool2 = nn.MaxPool2d((1, 4))
+            self.conv3 = nn.Conv2d(4, 8, (1, 10))
+            self.conv4 = nn.Conv2d(8, 8, (7, 1), padding=(3, 0))
+            self.maxpool3 = nn.MaxPool1d(98)
+            self.dropout = nn.Dropout()
+            self.fc1 = nn.Linear(8, 8)
+            self.fc2 = nn.Linear(8, 12)
+
+        def forward(self, x):
+            with torch.no_grad():
+                inx = torch.ones(x.size(0), 98, 120)
+                for i in range(x.size(0)):
+                    inx[i] = m.filter_banks(x[i])
+            inx = inx.to(next(self.parameters()).device)
+            return patch._cnn_tail(self, inx)
+
+    m.filter_banks, m.Network = filter_banks, Network
+    return m
+
+
+@pytest.mark.parametrize("factory,kind", [(_standin_mfcc_bgru, "mfcc_bgru"), (_standin_fbanks_cnn, "fbanks_cnn")])
+def test_standin_cpu(factory, kind):
+    mod = factory()
+    assert patch.detect_kind(mod) == kind
+    torch.manual_seed(1)
+    net = mod.Network().eval()
+    x = torch.from_numpy(oracle.synthetic_corpus(2, config_index=7))
+    with torch.no_grad():
+        want = net(x)
+    patch.patch_model(mod, feature_fn=_oracle_fn(kind))
+    with torch.no_grad():
+        got = net(x)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    assert mod.Network.forward.__srfe_patched__ == kind
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("factory,kind", [(_standin_mfcc_bgru, "mfcc_bgru"), (_standin_fbanks_cnn, "fbanks_cnn")])
+def test_standin_gpu_real_kernels(srfe_lib, factory, kind):
+    mod = factory()
+    torch.manual_seed(2)
+    net = mod.Network().eval()
+    x = torch.from_numpy(oracle.synthetic_corpus(4, config_index=8))
+    with torch.no_grad():
+        want = net(x)                                  # CPU loop with oracle features
+    net = net.cuda()
+    patch.patch_model(mod)                             # default: fused CUDA features, PCM H2D only
+    with torch.no_grad():
+        got_host_pcm = net(x)                          # CPU batch, like DataLoader hands it over
+        got_dev_pcm = net(x.cuda())                    # PCM already resident
+    assert got_host_pcm.is_cuda and torch.equal(got_host_pcm, got_dev_pcm)
+    torch.testing.assert_close(got_host_pcm.cpu(), want, rtol=2e-3, atol=2e-3)
