@@ -8,7 +8,10 @@ names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(S.PRESETS)
 x = (torch.randn(B, 16000, device="cuda") * 3000).round()
 PEAK = 6460.5
 for name in names:
-    p = S.PRESETS[name]
+    from dataclasses import replace
+    base, _, lay = name.partition(":")
+    p = S.PRESETS[base]
+    if lay: p = replace(p, layout=lay)
     fn = {"SpecParams": S.spec, "FbankParams": S.fbank, "MfccParams": S.mfcc}[type(p).__name__]
     for _ in range(3):
         y = fn(x, p)

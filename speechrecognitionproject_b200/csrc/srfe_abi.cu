@@ -1,7 +1,9 @@
 // srfe_abi.cu -- the extern "C" boundary declared in include/srfe.h: parameter
 // validation, the per-(device, parameter set) table cache, kernel launches and
 // the host-buffer entry points (H2D -> kernel -> D2H, chunked over two streams).
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -53,7 +55,7 @@ struct Key {
 
 static std::mutex g_mu;
 static std::map<Key, Entry*> g_cache;
-static std::map<const void*, bool> g_attr_set;     // kernel function -> max-smem attribute raised (per process)
+static std::map<const void*, int> g_attr_set;      // kernel function -> max-smem attribute raised (per process)
 
 static int align16(int x) { return (x + 15) & ~15; }
 
@@ -106,13 +108,18 @@ static void add_fft_tables(BlobBuilder& bb, KParams& kp, int n_fft, const std::v
     window_range(win, kp.w_lo, kp.w_hi);
 }
 
-static void add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb) {
-    std::vector<int32_t> meta(sb.start.size());
-    for (size_t i = 0; i < meta.size(); ++i)                         // start | count << 10 | offset << 18
-        meta[i] = (sb.start[i] & 0x3ff) | ((sb.count[i] & 0xff) << 10) | (sb.offset[i] << 18);
-    kp.off_fm = bb.add(meta.data(), meta.size() * 4);
-    kp.off_fw = bb.add(sb.weight.data(), sb.weight.size() * 4);
+static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_fft) {
+    EllBank ell;
+    to_ell(sb, ell);
+    // the packed power buffer aliases the FFT scratch: the padded runs must stay inside it
+    const int cap = (n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 2;    // P2 slots
+    if (ell.max_reach > cap) return fail(SRFE_ERR_UNSUPPORTED, "filterbank too wide for the shared-memory power buffer");
+    kp.off_gm = bb.add(ell.gmeta.data(), ell.gmeta.size() * 4);
+    kp.off_fs = bb.add(ell.start.data(), ell.start.size() * 4);
+    kp.off_fw4 = bb.add(ell.w4.data(), ell.w4.size() * 4);
     kp.n_filt = (int)sb.start.size();
+    kp.n_fgroups = ell.groups;
+    return SRFE_OK;
 }
 
 static int build_entry(const srfe_spec_params& p, Entry* e);
@@ -164,7 +171,7 @@ static int build_entry(const srfe_fbank_params& p, Entry* e) {
     to_sparse(dense, p.nfilt, p.n_fft / 2 + 1, 0.25 / (double)p.n_fft, sb);   // |X|^2 / NFFT (model_fbanks_cnn.py:43)
     BlobBuilder bb;
     add_fft_tables(bb, e->kp, p.n_fft, win);
-    add_bank(bb, e->kp, sb);
+    { int rc = add_bank(bb, e->kp, sb, p.n_fft); if (rc != SRFE_OK) return rc; }
     e->n_fft = p.n_fft;
     e->n_bins = p.n_fft / 2 + 1;
     e->kp.hop = p.frame_step;
@@ -183,7 +190,7 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     to_sparse(dense, p.n_mels, p.n_fft / 2 + 1, 0.25, sb);
     BlobBuilder bb;
     add_fft_tables(bb, e->kp, p.n_fft, win);
-    add_bank(bb, e->kp, sb);
+    { int rc = add_bank(bb, e->kp, sb, p.n_fft); if (rc != SRFE_OK) return rc; }
     e->n_fft = p.n_fft;
     e->n_bins = p.n_fft / 2 + 1;
     e->kp.hop = p.hop;
@@ -214,17 +221,33 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
 // ------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------
-template <int NFFT, int FAM, int JLO, int JHI>
-static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI>;
+struct DevInfo { int sms = 0; int smem_optin = 0; };
+static DevInfo g_dev[64];
+
+static int dev_info(DevInfo** out) {
+    int dev = 0;
+    SRFE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].sms == 0) {
+        SRFE_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+        SRFE_CUDA(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    }
+    *out = &g_dev[dev];
+    return SRFE_OK;
+}
+
+template <int NFFT, int FAM, int JLO, int JHI, int MAXT, bool PF>
+static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, MAXT, PF>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
         cudaGetDevice(&dev);
         const void* tag = (const char*)(const void*)kern + dev;      // per (kernel, device)
-        if (!g_attr_set.count(tag)) {
-            SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            g_attr_set[tag] = true;
+        if (g_attr_set[tag] < smem_bytes) {                          // raise the opt-in limit on demand
+            SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            g_attr_set[tag] = smem_bytes;
         }
     }
     kern<<<grid, threads, smem_bytes, st>>>(kp);
@@ -234,34 +257,24 @@ static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, cu
     return SRFE_OK;
 }
 
-// Slots per CTA (S, even, <= 16) and clips per CTA so that cpc*T fills whole rounds of S
-// frames: score = round efficiency x a mild preference for more resident warps.
-static void pick_config(int family, int T, int n_clips, int* S_out, int* cpc_out) {
-    double best = -1.0;
-    int bs = kMaxSlots, bc = 1;
-    const int cpc_max = (family == FAM_MFCC) ? 1 : 4;
-    for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
-        if (cpc > 1 && cpc > n_clips) break;
-        for (int S = kMaxSlots; S >= 8; S -= 2) {
-            const long long nf = (long long)cpc * T;
-            const long long rounds = (nf + S - 1) / S;
-            double score = (double)nf / (double)(rounds * S);
-            score *= 0.75 + 0.25 * (double)S / kMaxSlots;
-            score *= 1.0 - 0.005 * (cpc - 1);
-            if (score > best + 1e-9) { best = score; bs = S; bc = cpc; }
-        }
-    }
-    *S_out = bs;
-    *cpc_out = bc;
+template <int NFFT, int FAM, int JLO, int JHI>
+static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, bool prefetch, cudaStream_t st) {
+    if (prefetch && threads <= 384) return launch_k<NFFT, FAM, JLO, JHI, 384, true>(kp, grid, threads, smem_bytes, st);
+    return launch_k<NFFT, FAM, JLO, JHI, 512, false>(kp, grid, threads, smem_bytes, st);
 }
 
-static int launch(const Entry* e, KParams kp, cudaStream_t st) {
-    int S = kMaxSlots, cpc = 1;
-    pick_config(e->family, kp.T, kp.n_clips, &S, &cpc);
-    kp.cpc = cpc;
-    int scratch = S * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_CPX : FftGeom<640>::SCRATCH_CPX) * 8;
+struct Config { int warps, ctas, cpc, smem, scratch, tile; };
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// shared memory of a CTA with `warps` warps; returns total bytes, fills scratch/tile sizes
+static int smem_for(const Entry* e, const KParams& kp, int warps, int* scratch_out, int* tile_out) {
+    const int hw = 2 * warps;
+    int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 16;
     int tile = 0;
-    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT) tile = 2 * e->n_bins * (S + 1) * 4;   // double-buffered
     if (e->family == FAM_MFCC) {
         tile = kp.T * kp.tile_stride * 4 + kp.T * 4;                 // dB tile + per-frame means
         const int TC = kp.T + 1;
@@ -269,19 +282,72 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
         // reach into the dB tile; the delta rows may (the tile is dead by then)
         const int dtab = kp.use_mma ? kp.nt8 * 8 * (kp.n_filt + 4) * 4 : 0;
         if (dtab + kp.n_mfcc * TC * 4 > scratch) scratch = align16(dtab + kp.n_mfcc * TC * 4);
-        if (dtab + (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile))
-            return fail(SRFE_ERR_TOO_LARGE, "mfcc: coefficient tile does not fit the per-clip shared memory budget");
-        if (kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
+        if (dtab + (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile)) return -1;
     }
-    kp.sm_scratch = align16(e->blob_smem);
-    kp.sm_tile = kp.sm_scratch + scratch;
-    const int smem = kp.sm_tile + align16(tile);
-    if (smem > 200 * 1024) return fail(SRFE_ERR_TOO_LARGE, "clip too long: per-clip tile exceeds shared memory");
+    *scratch_out = scratch;
+    *tile_out = align16(tile);
+    return align16(e->blob_smem) + scratch + align16(tile);
+}
+
+// Warps per CTA, CTAs per SM and clips per group: fill whole rounds of 4*warps frames, keep as many
+// warps resident as the shared-memory budget allows, prefer two CTAs per SM (their phases overlap).
+static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Config* out) {
+    double best = -1.0;
+    Config bc{0, 0, 1, 0, 0, 0};
+    const int cpc_max = (e->family == FAM_MFCC) ? 1 : 8;
+    const int per_sm = 228 * 1024;                                   // B200: 228 KB per SM, 1 KB reserved per CTA
+    for (int ctas = 1; ctas <= 2; ++ctas) {
+        const int budget = std::min(di.smem_optin, per_sm / ctas - 1024);
+        for (int warps = (ctas == 1 ? 8 : 4); warps <= (ctas == 1 ? 16 : 8); ++warps) {
+            int scratch = 0, tile = 0;
+            const int smem = smem_for(e, kp, warps, &scratch, &tile);
+            if (smem < 0 || smem > budget) continue;
+            for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
+                if (cpc > 1 && cpc > kp.n_clips) break;
+                const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
+                const long long rounds = (nf + per_round - 1) / per_round;
+                double score = (double)nf / (double)(rounds * per_round);
+                score *= 0.55 + 0.45 * std::min(16, ctas * warps) / 16.0;
+                if (ctas == 1) score *= 0.94;
+                score *= 1.0 - 0.004 * (cpc - 1);
+                if (score > best + 1e-9) { best = score; bc = Config{warps, ctas, cpc, smem, scratch, tile}; }
+            }
+        }
+    }
+    if (best < 0) return fail(SRFE_ERR_TOO_LARGE, "clip too long: the per-clip tile does not fit in shared memory");
+    // developer overrides (tuning only)
+    const int ow = env_int("SRFE_WARPS", 0), oc = env_int("SRFE_CTAS", 0), op = env_int("SRFE_CPC", 0);
+    if (ow > 0 || oc > 0 || op > 0) {
+        if (ow > 0) bc.warps = std::min(16, std::max(1, ow));
+        if (oc > 0) bc.ctas = std::min(8, std::max(1, oc));
+        if (op > 0 && e->family != FAM_MFCC) bc.cpc = op;
+        bc.smem = smem_for(e, kp, bc.warps, &bc.scratch, &bc.tile);
+        if (bc.smem < 0 || bc.smem > di.smem_optin) return fail(SRFE_ERR_TOO_LARGE, "SRFE_WARPS override does not fit in shared memory");
+    }
+    *out = bc;
+    return SRFE_OK;
+}
+
+static int launch(const Entry* e, KParams kp, cudaStream_t st) {
+    if (e->family == FAM_MFCC && kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
     if (kp.n_clips == 0 || kp.T == 0) return SRFE_OK;
-    const int grid = (kp.n_clips + cpc - 1) / cpc, threads = 16 * S;
+    DevInfo* di = nullptr;
+    int rc = dev_info(&di);
+    if (rc != SRFE_OK) return rc;
+    Config cfg;
+    rc = pick_config(e, kp, *di, &cfg);
+    if (rc != SRFE_OK) return rc;
+    kp.cpc = cfg.cpc;
+    kp.n_groups = (kp.n_clips + cfg.cpc - 1) / cfg.cpc;
+    kp.sm_scratch = align16(e->blob_smem);
+    kp.sm_tile = kp.sm_scratch + cfg.scratch;
+    const int smem = cfg.smem;
+    const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
     // window extent in units of 32 samples; known extents get a specialised instantiation
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
-#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(kp, grid, threads, smem, st)
+    // register-prefetch flavour (168 regs): only when all resident warps fit the register file
+    const bool prefetch = env_int("SRFE_PREFETCH", 0) != 0 && cfg.ctas * cfg.warps <= 12;
+#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(kp, grid, threads, smem, prefetch, st)
     if (e->n_fft == 512) {
         switch (e->family) {
             case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16);

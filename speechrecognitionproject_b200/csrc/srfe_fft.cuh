@@ -1,21 +1,25 @@
-// srfe_fft.cuh -- register DFT codelets and the half-warp real-FFT pipeline.
+// srfe_fft.cuh -- register DFT codelets and the half-warp real-FFT pipeline,
+// TWO FRAMES PER LANE in packed f32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2).
 //
-// One analysis frame (real, N = 512 or 640 points after windowing / zero padding)
-// is transformed by 16 lanes (half a warp; a warp carries two frames):
+// A half-warp (16 lanes) transforms a PAIR of analysis frames (A, B) at once: every
+// value is a P2 = (frame A, frame B) register pair and every butterfly is one packed
+// instruction, so FP issue slots, shared-memory instructions and address arithmetic per
+// frame are halved (the FP32 pipe itself still retires 128 lane-ops/clk/SM -- measured,
+// scripts/ubench/fp32x2.cu -- which is what finally bounds this path).
 //
 //   z[m] = xw[2m] + i xw[2m+1]           M = N/2 complex points, V = M/16 per lane
 //   pass 1   lane l: DFT-V over m = l + 16 j        (registers)
-//   twiddle  W_M^{l k1}                              (table in shared memory)
-//   exchange through a padded shared-memory tile     (STS.64 / LDS.128)
+//   twiddle  W_M^{l k1}                              (scalar table in shared memory, broadcast operand)
+//   exchange through a padded shared-memory tile     (one 16-byte C2 per point: STS.128 / LDS.128)
 //   pass 2   M=256: one DFT-16 per lane              (registers)
-//            M=320: DFT-16 = two radix-4 passes with a second exchange
+//            M=320: DFT-16 = two radix-4 passes with a second (skewed) exchange
 //   Z[k] -> shared, natural order
 //   untangle lane takes the pairs (k, M-k), k = l + 16 r: one twiddle per pair,
-//            yields |X[k]|^2 and |X[M-k]|^2 (x4, the 1/4 is folded downstream)
+//            yields 4|X[k]|^2 and 4|X[M-k]|^2 (the 1/4 is folded downstream)
 //
-// Everything here is __host__ __device__ and free of warp intrinsics so that
-// tests/emu can run the identical index arithmetic lane by lane on the CPU
-// (phases are separated by warp syncs on the device, by loops on the host).
+// Everything is __host__ __device__ and free of warp intrinsics so tests/emu runs the
+// identical index arithmetic lane by lane on the CPU (phases are separated by warp
+// syncs on the device, by loops on the host).
 #pragma once
 
 #include <vector_types.h>
@@ -28,93 +32,117 @@
 
 namespace srfe {
 
-typedef float2 cpx;
+// ---- packed pair (frame A, frame B) ------------------------------------------------
+struct __align__(8) P2 { float lo, hi; };
 
-SRFE_HD cpx mk(float x, float y) { cpx r; r.x = x; r.y = y; return r; }
-SRFE_HD cpx cadd(cpx a, cpx b) { return mk(a.x + b.x, a.y + b.y); }
-SRFE_HD cpx csub(cpx a, cpx b) { return mk(a.x - b.x, a.y - b.y); }
-SRFE_HD cpx cmul(cpx a, cpx w) { return mk(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
-SRFE_HD cpx mul_mi(cpx a) { return mk(a.y, -a.x); }                       // a * (-i)
+#if defined(__CUDA_ARCH__)
+#define SRFE_U64(p) (*reinterpret_cast<unsigned long long*>(&(p)))
+#define SRFE_CU64(p) (*reinterpret_cast<const unsigned long long*>(&(p)))
+SRFE_HD P2 padd(const P2& a, const P2& b) { P2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(SRFE_U64(d)) : "l"(SRFE_CU64(a)), "l"(SRFE_CU64(b))); return d; }
+SRFE_HD P2 psub(const P2& a, const P2& b) { P2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(SRFE_U64(d)) : "l"(SRFE_CU64(a)), "l"(SRFE_CU64(b))); return d; }
+SRFE_HD P2 pmul(const P2& a, const P2& b) { P2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(SRFE_U64(d)) : "l"(SRFE_CU64(a)), "l"(SRFE_CU64(b))); return d; }
+SRFE_HD P2 pfma(const P2& a, const P2& b, const P2& c) { P2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(SRFE_U64(d)) : "l"(SRFE_CU64(a)), "l"(SRFE_CU64(b)), "l"(SRFE_CU64(c))); return d; }
+#else
+SRFE_HD P2 padd(const P2& a, const P2& b) { P2 d; d.lo = a.lo + b.lo; d.hi = a.hi + b.hi; return d; }
+SRFE_HD P2 psub(const P2& a, const P2& b) { P2 d; d.lo = a.lo - b.lo; d.hi = a.hi - b.hi; return d; }
+SRFE_HD P2 pmul(const P2& a, const P2& b) { P2 d; d.lo = a.lo * b.lo; d.hi = a.hi * b.hi; return d; }
+SRFE_HD P2 pfma(const P2& a, const P2& b, const P2& c) { P2 d; d.lo = a.lo * b.lo + c.lo; d.hi = a.hi * b.hi + c.hi; return d; }
+#endif
+SRFE_HD P2 bc(float s) { P2 d; d.lo = s; d.hi = s; return d; }                 // scalar -> both frames (FFMA2 .F32 operand)
+SRFE_HD P2 mkp(float a, float b) { P2 d; d.lo = a; d.hi = b; return d; }
+
+// ---- packed complex: 16 bytes, the unit of every shared-memory exchange ----------------
+struct __align__(16) C2 { P2 re, im; };
+typedef float2 cpx;                                                             // scalar complex (twiddle tables)
+
+SRFE_HD C2 cadd(const C2& a, const C2& b) { C2 d; d.re = padd(a.re, b.re); d.im = padd(a.im, b.im); return d; }
+SRFE_HD C2 csub(const C2& a, const C2& b) { C2 d; d.re = psub(a.re, b.re); d.im = psub(a.im, b.im); return d; }
+// a * (wr + i wi), scalar twiddle shared by both frames: 2 FMUL2 + 2 FFMA2
+SRFE_HD C2 cmuls(const C2& a, float wr, float wi) {
+    const P2 WR = bc(wr), WI = bc(wi), NWI = bc(-wi);
+    C2 d;
+    d.re = pfma(a.im, NWI, pmul(a.re, WR));
+    d.im = pfma(a.re, WI, pmul(a.im, WR));
+    return d;
+}
 #define SRFE_SQRT1_2 0.70710678118654752440f
-SRFE_HD cpx mul_w8_1(cpx a) { return mk((a.x + a.y) * SRFE_SQRT1_2, (a.y - a.x) * SRFE_SQRT1_2); }   // a * W8^1
-SRFE_HD cpx mul_w8_3(cpx a) { return mk((a.y - a.x) * SRFE_SQRT1_2, -(a.x + a.y) * SRFE_SQRT1_2); }  // a * W8^3
+SRFE_HD C2 mul_w8_1(const C2& a) { C2 d; const P2 c = bc(SRFE_SQRT1_2); d.re = pmul(padd(a.re, a.im), c); d.im = pmul(psub(a.im, a.re), c); return d; }   // a * W8^1
+SRFE_HD C2 mul_w8_3(const C2& a) { C2 d; d.re = pmul(psub(a.im, a.re), bc(SRFE_SQRT1_2)); d.im = pmul(padd(a.re, a.im), bc(-SRFE_SQRT1_2)); return d; }   // a * W8^3
+SRFE_HD C2 mul_mi(const C2& a) { C2 d; d.re = a.im; d.im = psub(bc(0.f), a.re); return d; }                                                                // a * (-i)
 
-// ---- forward DFT codelets (e^{-2 pi i nk/N}), in place, natural order out ----
-SRFE_HD void dft2(cpx& a, cpx& b) { cpx t = csub(a, b); a = cadd(a, b); b = t; }
-
-SRFE_HD void dft4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
-    cpx t0 = cadd(a0, a2), t1 = csub(a0, a2);
-    cpx t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+// ---- forward DFT codelets (e^{-2 pi i nk/N}), in place, natural order out --------------
+SRFE_HD void dft4(C2& a0, C2& a1, C2& a2, C2& a3) {
+    const C2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+    C2 t3;                                               // (a1 - a3) * (-i), no explicit negation
+    t3.re = psub(a1.im, a3.im);
+    t3.im = psub(a3.re, a1.re);
     a0 = cadd(t0, t2); a2 = csub(t0, t2);
     a1 = cadd(t1, t3); a3 = csub(t1, t3);
 }
 
-SRFE_HD void dft5(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4) {
-    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    cpx t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
-    cpx m1 = mk(a0.x + c1 * t1.x + c2 * t2.x, a0.y + c1 * t1.y + c2 * t2.y);
-    cpx m2 = mk(a0.x + c2 * t1.x + c1 * t2.x, a0.y + c2 * t1.y + c1 * t2.y);
-    cpx n1 = mk(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    cpx n2 = mk(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-    a0 = mk(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-    a1 = mk(m1.x + n1.y, m1.y - n1.x);        // m1 - i n1
-    a4 = mk(m1.x - n1.y, m1.y + n1.x);        // m1 + i n1
-    a2 = mk(m2.x + n2.y, m2.y - n2.x);
-    a3 = mk(m2.x - n2.y, m2.y + n2.x);
+SRFE_HD void dft5(C2& a0, C2& a1, C2& a2, C2& a3, C2& a4) {
+    const P2 c1 = bc(0.30901699437494742410f), c2 = bc(-0.80901699437494742410f);
+    const P2 s1 = bc(0.95105651629515357212f), s2 = bc(0.58778525229247312917f), ns1 = bc(-0.95105651629515357212f);
+    const C2 t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+    C2 m1, m2, n1, n2;
+    m1.re = pfma(c2, t2.re, pfma(c1, t1.re, a0.re)); m1.im = pfma(c2, t2.im, pfma(c1, t1.im, a0.im));
+    m2.re = pfma(c1, t2.re, pfma(c2, t1.re, a0.re)); m2.im = pfma(c1, t2.im, pfma(c2, t1.im, a0.im));
+    n1.re = pfma(s2, t4.re, pmul(s1, t3.re));        n1.im = pfma(s2, t4.im, pmul(s1, t3.im));
+    n2.re = pfma(ns1, t4.re, pmul(s2, t3.re));       n2.im = pfma(ns1, t4.im, pmul(s2, t3.im));
+    a0.re = padd(a0.re, padd(t1.re, t2.re)); a0.im = padd(a0.im, padd(t1.im, t2.im));
+    a1.re = padd(m1.re, n1.im); a1.im = psub(m1.im, n1.re);        // m1 - i n1
+    a4.re = psub(m1.re, n1.im); a4.im = padd(m1.im, n1.re);        // m1 + i n1
+    a2.re = padd(m2.re, n2.im); a2.im = psub(m2.im, n2.re);
+    a3.re = psub(m2.re, n2.im); a3.im = padd(m2.im, n2.re);
 }
 
 // 16-point: n = n1 + 4 n2, k = ka + 4 kb; constant twiddles W16^{n1 ka}
-SRFE_HD void dft16(cpx* v) {
-    const cpx w1 = mk(0.92387953251128675613f, -0.38268343236508977173f);
-    const cpx w3 = mk(0.38268343236508977173f, -0.92387953251128675613f);
-    const cpx w9 = mk(-0.92387953251128675613f, 0.38268343236508977173f);
+SRFE_HD void dft16(C2* v) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
 #pragma unroll
     for (int n1 = 0; n1 < 4; ++n1) dft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
     // v[n1 + 4 ka] holds T[n1][ka]
-    v[1 + 4] = cmul(v[1 + 4], w1);      v[1 + 8] = mul_w8_1(v[1 + 8]);          v[1 + 12] = cmul(v[1 + 12], w3);
-    v[2 + 4] = mul_w8_1(v[2 + 4]);      v[2 + 8] = mul_mi(v[2 + 8]);            v[2 + 12] = mul_w8_3(v[2 + 12]);
-    v[3 + 4] = cmul(v[3 + 4], w3);      v[3 + 8] = mul_w8_3(v[3 + 8]);          v[3 + 12] = cmul(v[3 + 12], w9);
+    v[1 + 4] = cmuls(v[1 + 4], c1, -s1);  v[1 + 8] = mul_w8_1(v[1 + 8]);   v[1 + 12] = cmuls(v[1 + 12], s1, -c1);
+    v[2 + 4] = mul_w8_1(v[2 + 4]);        v[2 + 8] = mul_mi(v[2 + 8]);     v[2 + 12] = mul_w8_3(v[2 + 12]);
+    v[3 + 4] = cmuls(v[3 + 4], s1, -c1);  v[3 + 8] = mul_w8_3(v[3 + 8]);   v[3 + 12] = cmuls(v[3 + 12], -c1, s1);
 #pragma unroll
     for (int ka = 0; ka < 4; ++ka) dft4(v[4 * ka], v[4 * ka + 1], v[4 * ka + 2], v[4 * ka + 3]);
-    // v[kb + 4 ka] holds X[ka + 4 kb]  -> transpose to natural order
+    // v[kb + 4 ka] holds X[ka + 4 kb]  -> transpose to natural order (register renaming)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = a + 1; b < 4; ++b) { cpx t = v[b + 4 * a]; v[b + 4 * a] = v[a + 4 * b]; v[a + 4 * b] = t; }
+        for (int b = a + 1; b < 4; ++b) { const C2 t = v[b + 4 * a]; v[b + 4 * a] = v[a + 4 * b]; v[a + 4 * b] = t; }
 }
 
-// 20-point, Good-Thomas 4 x 5 (no internal twiddles):
-//   n = (5 n1 + 4 n2) mod 20,  k = (5 k1 + 16 k2) mod 20
-SRFE_HD void dft20(cpx* v) {
-    cpx u[20];
+// 20-point, Good-Thomas 4 x 5 (no internal twiddles), in place:
+//   n = (5 n1 + 4 n2) mod 20 ; X[(5 k1 + 16 k2) mod 20] ends up at position (5 k1 + 4 k2) mod 20
+SRFE_HD void dft20(C2* v) {
 #pragma unroll
-    for (int n1 = 0; n1 < 4; ++n1)
+    for (int n2 = 0; n2 < 5; ++n2)
+        dft4(v[(4 * n2) % 20], v[(5 + 4 * n2) % 20], v[(10 + 4 * n2) % 20], v[(15 + 4 * n2) % 20]);       // over n1 -> k1
 #pragma unroll
-        for (int n2 = 0; n2 < 5; ++n2) u[n1 * 5 + n2] = v[(5 * n1 + 4 * n2) % 20];
+    for (int k1 = 0; k1 < 4; ++k1)
+        dft5(v[(5 * k1) % 20], v[(5 * k1 + 4) % 20], v[(5 * k1 + 8) % 20], v[(5 * k1 + 12) % 20], v[(5 * k1 + 16) % 20]);
+    C2 u[20];
 #pragma unroll
-    for (int n2 = 0; n2 < 5; ++n2) dft4(u[n2], u[5 + n2], u[10 + n2], u[15 + n2]);       // over n1 -> k1
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) dft5(u[5 * k1], u[5 * k1 + 1], u[5 * k1 + 2], u[5 * k1 + 3], u[5 * k1 + 4]);
+    for (int i = 0; i < 20; ++i) u[i] = v[i];
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1)
 #pragma unroll
-        for (int k2 = 0; k2 < 5; ++k2) v[(5 * k1 + 16 * k2) % 20] = u[k1 * 5 + k2];
+        for (int k2 = 0; k2 < 5; ++k2) v[(5 * k1 + 16 * k2) % 20] = u[(5 * k1 + 4 * k2) % 20];
 }
 
-// ---- geometry of the half-warp FFT -------------------------------------------
+// ---- geometry of the half-warp FFT ---------------------------------------------------
 template <int NFFT> struct FftGeom;
 template <> struct FftGeom<512> {
     static constexpr int N = 512, M = 256, L = 16, V = 16;
-    static constexpr int XS = 18;                 // exchange row stride (cpx): LDS.128 conflict-free
-    static constexpr int XROWS = 16;
-    static constexpr int SCRATCH_CPX = 288;       // max(XROWS*XS, M)
+    static constexpr int XS = 17;                 // exchange row stride (C2 units): odd -> LDS.128 conflict-free
+    static constexpr int SCRATCH_C2 = 16 * 17;    // >= M (zbuf) and >= (M + 1 + 16) / 2 (packed power buffer)
 };
 template <> struct FftGeom<640> {
     static constexpr int N = 640, M = 320, L = 16, V = 20;
-    static constexpr int XS = 18;
-    static constexpr int XROWS = 20;
-    static constexpr int SCRATCH_CPX = 360;
+    static constexpr int XS = 20;                 // = 4 (mod 8): both radix-4 gathers conflict-free
+    static constexpr int SCRATCH_C2 = 20 * 20;
 };
 
 // Twiddle tables a CTA keeps in shared memory (built on the host in double):
@@ -127,77 +155,75 @@ struct FftTables {
     const cpx* tw16;
 };
 
-// ---- phase 1: DFT-V, twiddle, scatter into the exchange tile -------------------
+// ---- phase 1: DFT-V, twiddle, scatter into the exchange tile (row k1, column l) --------
 template <int NFFT>
-SRFE_HD void fft_phase1(cpx* v, int l, cpx* xbuf, const FftTables& T) {
+SRFE_HD void fft_phase1(C2* v, int l, C2* xbuf, const FftTables& T) {
     typedef FftGeom<NFFT> G;
     if (G::V == 16) dft16(v); else dft20(v);
+    xbuf[l] = v[0];
 #pragma unroll
-    for (int k1 = 0; k1 < G::V; ++k1) {
-        cpx a = (k1 == 0) ? v[0] : cmul(v[k1], T.tw1[k1 * 16 + l]);
-        int col = (NFFT == 640) ? ((l & 3) * 4 + (l >> 2)) : l;     // M=320: l = l1 + 4 l2 -> 4 l1 + l2
-        xbuf[k1 * G::XS + col] = a;
+    for (int k1 = 1; k1 < G::V; ++k1) {
+        const cpx w = T.tw1[k1 * 16 + l];
+        xbuf[k1 * G::XS + l] = cmuls(v[k1], w.x, w.y);
     }
 }
 
-// ---- phase 2 (N=512): one DFT-16 per lane, Z out in natural order ---------------
-SRFE_HD void fft_phase2_512(int l, const cpx* xbuf, cpx* v) {
+// ---- phase 2 (N=512): one DFT-16 per lane, Z out in natural order ------------------------
+SRFE_HD void fft_phase2_512(int l, const C2* xbuf, C2* v) {
     typedef FftGeom<512> G;
-    const float4* row = reinterpret_cast<const float4*>(xbuf + l * G::XS);     // 144 B rows: 16 B aligned
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float4 q = row[i]; v[2 * i] = mk(q.x, q.y); v[2 * i + 1] = mk(q.z, q.w); }
+    for (int i = 0; i < 16; ++i) v[i] = xbuf[l * G::XS + i];
     dft16(v);                                   // v[k2] = Z[l + 16 k2]
 }
-SRFE_HD void fft_store_z_512(int l, const cpx* v, cpx* zbuf) {
+SRFE_HD void fft_store_z_512(int l, const C2* v, C2* zbuf) {
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) zbuf[l + 16 * k2] = v[k2];
 }
 
-// ---- phases 2/3 (N=640): DFT-16 over l = l1 + 4 l2 as two radix-4 passes -------
+// ---- phases 2/3 (N=640): DFT-16 over l = l1 + 4 l2 as two radix-4 passes -----------------
 // lane = a + 4 b.  pass 2: l1 = a, k1 = b + 4 i (i<5), DFT-4 over l2 -> k2a.
-SRFE_HD void fft_phase2_640(int lane, const cpx* xbuf, cpx* v, const FftTables& T) {
+SRFE_HD void fft_phase2_640(int lane, const C2* xbuf, C2* v, const FftTables& T) {
     typedef FftGeom<640> G;
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const float4* row = reinterpret_cast<const float4*>(xbuf + (b + 4 * i) * G::XS + 4 * a);
-        const float4 q0 = row[0], q1 = row[1];
-        v[4 * i] = mk(q0.x, q0.y); v[4 * i + 1] = mk(q0.z, q0.w);
-        v[4 * i + 2] = mk(q1.x, q1.y); v[4 * i + 3] = mk(q1.z, q1.w);
+        const C2* row = xbuf + (b + 4 * i) * G::XS + a;
+#pragma unroll
+        for (int l2 = 0; l2 < 4; ++l2) v[4 * i + l2] = row[4 * l2];
         dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);      // index = k2a
     }
     const cpx t1 = T.tw16[a * 4 + 1], t2 = T.tw16[a * 4 + 2], t3 = T.tw16[a * 4 + 3];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        v[4 * i + 1] = cmul(v[4 * i + 1], t1);
-        v[4 * i + 2] = cmul(v[4 * i + 2], t2);
-        v[4 * i + 3] = cmul(v[4 * i + 3], t3);
+        v[4 * i + 1] = cmuls(v[4 * i + 1], t1.x, t1.y);
+        v[4 * i + 2] = cmuls(v[4 * i + 2], t2.x, t2.y);
+        v[4 * i + 3] = cmuls(v[4 * i + 3], t3.x, t3.y);
     }
 }
-// second exchange: row k1, column 4 k2a + a
-SRFE_HD void fft_scatter2_640(int lane, const cpx* v, cpx* xbuf) {
+// second exchange: element (l1 = a, k2a = c) of row k1 lives at column 4 c + ((a + c) & 3)
+// (skewed so that the 8-lane phases of both the scatter and the gather hit 8 distinct 16-byte banks)
+SRFE_HD void fft_scatter2_640(int lane, const C2* v, C2* xbuf) {
     typedef FftGeom<640> G;
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xbuf[(b + 4 * i) * G::XS + 4 * c + a] = v[4 * i + c];
+        for (int c = 0; c < 4; ++c) xbuf[(b + 4 * i) * G::XS + 4 * c + ((a + c) & 3)] = v[4 * i + c];
 }
 // pass 3: lane = c + 4 b handles k2a = c, k1 = b + 4 i; DFT-4 over l1 -> k2b;
 // v[4 i + k2b] = Z[k1 + 20 (c + 4 k2b)]
-SRFE_HD void fft_phase3_640(int lane, const cpx* xbuf, cpx* v) {
+SRFE_HD void fft_phase3_640(int lane, const C2* xbuf, C2* v) {
     typedef FftGeom<640> G;
     const int c = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const float4* row = reinterpret_cast<const float4*>(xbuf + (b + 4 * i) * G::XS + 4 * c);
-        const float4 q0 = row[0], q1 = row[1];
-        v[4 * i] = mk(q0.x, q0.y); v[4 * i + 1] = mk(q0.z, q0.w);
-        v[4 * i + 2] = mk(q1.x, q1.y); v[4 * i + 3] = mk(q1.z, q1.w);
+        const C2* row = xbuf + (b + 4 * i) * G::XS + 4 * c;
+#pragma unroll
+        for (int l1 = 0; l1 < 4; ++l1) v[4 * i + l1] = row[(l1 + c) & 3];
         dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
 }
-SRFE_HD void fft_store_z_640(int lane, const cpx* v, cpx* zbuf) {
+SRFE_HD void fft_store_z_640(int lane, const C2* v, C2* zbuf) {
     const int c = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
@@ -205,33 +231,35 @@ SRFE_HD void fft_store_z_640(int lane, const cpx* v, cpx* zbuf) {
         for (int kb = 0; kb < 4; ++kb) zbuf[(b + 4 * i) + 20 * (c + 4 * kb)] = v[4 * i + kb];
 }
 
-// ---- untangle: 4|X[k]|^2 and 4|X[M-k]|^2 from Z[k], Z[(M-k) mod M] -------------
+// ---- untangle: 4|X[k]|^2 and 4|X[M-k]|^2 from Z[k], Z[(M-k) mod M] ---------------------
 // (k = 0 yields bins 0 and M; k = M/2 yields the same bin twice)
-SRFE_HD void untangle_pair(cpx zk, cpx zm, cpx w, float& pk, float& pm) {
-    const float ax = zk.x + zm.x, ay = zk.y - zm.y;
-    const float bx = zk.y + zm.y, by = zm.x - zk.x;      // (B.y, -B.x), B = zk - conj(zm)
-    const float cx = bx * w.x - by * w.y, cy = bx * w.y + by * w.x;
-    const float px = ax + cx, py = ay + cy, qx = ax - cx, qy = ay - cy;
-    pk = px * px + py * py;
-    pm = qx * qx + qy * qy;
+SRFE_HD void untangle_pair(const C2& zk, const C2& zm, float wr, float wi, P2& pk, P2& pm) {
+    const P2 ax = padd(zk.re, zm.re), ay = psub(zk.im, zm.im);
+    const P2 bx = padd(zk.im, zm.im), by = psub(zm.re, zk.re);      // (B.im, -B.re), B = zk - conj(zm)
+    const P2 WR = bc(wr), WI = bc(wi), NWI = bc(-wi);
+    const P2 cx = pfma(by, NWI, pmul(bx, WR)), cy = pfma(bx, WI, pmul(by, WR));
+    const P2 px = padd(ax, cx), py = padd(ay, cy), qx = psub(ax, cx), qy = psub(ay, cy);
+    pk = pfma(px, px, pmul(py, py));
+    pm = pfma(qx, qx, pmul(qy, qy));
 }
 
 // lane l takes k = l + 16 r, r < M/32: pa[r] = 4|X[k]|^2, pb[r] = 4|X[M-k]|^2
 // (lane 0, r = 0: pb[0] is the Nyquist bin M).  Returns 4|X[M/2]|^2 (valid on lane 0).
 template <int NFFT>
-SRFE_HD float fft_untangle(int l, const cpx* zbuf, const FftTables& T, float* pa, float* pb) {
+SRFE_HD P2 fft_untangle(int l, const C2* zbuf, const FftTables& T, P2* pa, P2* pb) {
     typedef FftGeom<NFFT> G;
 #pragma unroll
     for (int r = 0; r < G::M / 32; ++r) {
         const int k = l + 16 * r;
-        const cpx zk = zbuf[k];
-        const cpx zm = zbuf[(G::M - k) & (k == 0 ? 0 : 0x7fffffff)];
-        untangle_pair(zk, zm, T.twu[k], pa[r], pb[r]);
+        const C2 zk = zbuf[k];
+        const C2 zm = zbuf[(r == 0 && l == 0) ? 0 : G::M - k];
+        const cpx w = T.twu[k];
+        untangle_pair(zk, zm, w.x, w.y, pa[r], pb[r]);
     }
-    float pmid = 0.f;
+    P2 pmid = bc(0.f);
     if (l == 0) {
-        const cpx z = zbuf[G::M / 2];
-        pmid = 4.f * (z.x * z.x + z.y * z.y);
+        const C2 z = zbuf[G::M / 2];
+        pmid = pmul(bc(4.f), pfma(z.re, z.re, pmul(z.im, z.im)));
     }
     return pmid;
 }

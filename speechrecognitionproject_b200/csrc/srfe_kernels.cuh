@@ -1,24 +1,27 @@
-// srfe_kernels.cuh -- fused feature kernels for sm_100a.
+// srfe_kernels.cuh -- fused feature kernels for sm_100a (packed two-frames-per-lane version).
 //
-// One CTA owns `cpc` consecutive clips (1 for MFCC, 1..4 for SPEC/FBANK) and runs
-// S = blockDim/16 "slots" (half-warps).  Slot s takes the flattened frames
-// f = s, s+S, ... of the CTA's clips; S and cpc are picked on the host so that
-// cpc*T is (nearly) a multiple of S (e.g. T=49: S=14, cpc=2 -> 7 full rounds).
+// Persistent CTAs: grid = min(#clip groups, SMs x CTAs/SM); a CTA loops over groups of
+// `cpc` consecutive clips (1 for MFCC, 1..8 for SPEC/FBANK).  Inside a group the
+// flattened frames are taken two at a time: half-warp h of the CTA's HW = blockDim/16
+// half-warps processes the frame PAIRS q = h, h+HW, ... (frames 2q and 2q+1) with every
+// value held as an f32x2 register pair (srfe_fft.cuh).  HW and cpc are picked on the host
+// so that cpc*T fills whole rounds of 2*HW frames.
 //
 //   global PCM --LDG.64, coalesced (16 lanes x 8 B = one 128 B line per load; the
 //                2-2.5x frame overlap is served by L1/L2, HBM sees each sample once);
-//                the NEXT frame of the slot is fetched into registers while the
-//                current one is in its second FFT pass (software pipelining)
+//                the NEXT pair of the half-warp is fetched into registers while the
+//                current one is in its output stage (software pipelining)
 //     -> pre-emphasis (fbank, exact fp32 rounding) -> window (shared table)
-//     -> half-warp FFT (srfe_fft.cuh: registers + one/two shared-memory exchanges);
-//        the window extent [32 JLO, 32 JHI) is a template parameter, so the zero
-//        inputs of the 400-in-512 frames are constant-folded out of the first pass
-//     -> untangle -> power
-//     -> SPEC : scale, ln(. + eps)             -> global (TF) or double-buffered tile (FT)
-//        FBANK: sparse triangle sums, 20 log10 -> global [T][nfilt]
-//        MFCC : sparse Slaney sums, 10 log10   -> per-clip dB tile in shared memory
-//   MFCC epilogue (after a CTA barrier): clip max -> top_db clamp -> DCT-II ->
-//   np.gradient deltas -> coalesced store.  Only final features reach HBM.
+//     -> packed half-warp FFT (registers + one/two shared-memory exchanges); the window
+//        extent [32 JLO, 32 JHI) is a template parameter, so the zero inputs of the
+//        400-in-512 frames are constant-folded out of the first pass
+//     -> untangle -> power (both frames at once)
+//     -> SPEC : scale, ln(. + eps)              -> global (TF) or per-warp 4-frame staging (FT)
+//        FBANK: sparse triangle sums (uniform-trip ELL), 20 log10 -> global [T][nfilt]
+//        MFCC : sparse Slaney sums, 10 log10    -> per-clip dB tile in shared memory
+//   MFCC epilogue (CTA barrier): clip max -> top_db clamp -> DCT-II on tensor cores
+//   (3xTF32 mma.sync) -> np.gradient deltas -> coalesced store.  Only final features
+//   reach HBM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -31,8 +34,7 @@ namespace srfe {
 
 enum Family { FAM_SPEC = 0, FAM_FBANK = 1, FAM_MFCC = 2 };
 
-constexpr int kMaxThreads = 256;       // <= 8 warps = 16 slots per CTA
-constexpr int kMaxSlots = kMaxThreads / 16;
+constexpr int kMaxThreads = 512;       // <= 16 warps = 32 half-warps (64 frames in flight) per CTA
 
 struct KParams {
     const float* pcm;
@@ -40,11 +42,12 @@ struct KParams {
     long long clip_stride;
     int n_clips, n_samples;
     int T, hop, start0;
-    int cpc;                           // clips per CTA
-    const unsigned char* blob;         // tables, copied to shared memory by every CTA
+    int cpc, n_groups;                 // clips per group, number of groups
+    const unsigned char* blob;         // tables, copied to shared memory once per CTA
     int blob_bytes;                    // multiple of 16
-    int off_win, off_tw1, off_twu, off_tw16, off_fm, off_fw;   // fm: packed (start | count<<10 | offset<<18)
-    int n_filt;
+    int off_win, off_tw1, off_twu, off_tw16;
+    int off_gm, off_fs, off_fw4;       // mel ELL: int2 {w4 offset, n4} per 16-filter group; start bin per filter; float4 weights
+    int n_filt, n_fgroups;
     float scale, log_eps;
     int take_log, layout;
     float preemph;
@@ -54,7 +57,7 @@ struct KParams {
     const float* dct_kf;               // global [nt8*8][n_mels], zero-padded rows (tensor-core DCT path)
     int use_mma, nt8;                  // DCT on mma.sync 3xTF32 when n_mels % 8 == 0; nt8 = ceil(n_mfcc / 8)
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
-    int tile_stride;                   // MFCC dB tile row stride (floats), odd
+    int tile_stride;                   // MFCC dB tile row stride (floats)
     int w_lo, w_hi;                    // non-zero extent of the window (informational)
 };
 
@@ -105,23 +108,33 @@ __device__ __forceinline__ void fetch_frame(const KParams& p, const float* __res
     }
 }
 
-// v[j] = window[n] * s[n]; zero outside [JLO, JHI) (compile-time, folds into the DFT)
+template <int FAM, int NJ>
+__device__ __forceinline__ void emphasise(const KParams& p, const RawFrame<FAM, NJ>& r, int j, float& s0, float& s1) {
+    s0 = r.s[j].x;
+    s1 = r.s[j].y;
+    if (FAM == FAM_FBANK && !r.final_) {                    // float32, no FMA contraction
+        s1 = __fsub_rn(s1, __fmul_rn(p.preemph, s0));
+        s0 = __fsub_rn(s0, __fmul_rn(p.preemph, r.prev[j]));
+    }
+}
+
+// v[j] = window[n] * (sA[n], sB[n]); zero outside [JLO, JHI) (compile-time, folds into the DFT)
 template <int NFFT, int FAM, int JLO, int JHI>
-__device__ __forceinline__ void window_frame(const KParams& p, const RawFrame<FAM, JHI - JLO>& r, int l,
-                                             const float* s_win, cpx* v) {
+__device__ __forceinline__ void window_pair(const KParams& p, const RawFrame<FAM, JHI - JLO>& ra,
+                                            const RawFrame<FAM, JHI - JLO>& rb, int l, const float* s_win, C2* v) {
     typedef FftGeom<NFFT> G;
 #pragma unroll
     for (int j = 0; j < G::V; ++j) {
         if (j >= JLO && j < JHI) {
             const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * l + 32 * j);
-            float s0 = r.s[j - JLO].x, s1 = r.s[j - JLO].y;
-            if (FAM == FAM_FBANK && !r.final_) {            // float32, no FMA contraction
-                s1 = __fsub_rn(s1, __fmul_rn(p.preemph, s0));
-                s0 = __fsub_rn(s0, __fmul_rn(p.preemph, r.prev[j - JLO]));
-            }
-            v[j] = mk(w.x * s0, w.y * s1);
+            float a0, a1, b0, b1;
+            emphasise<FAM>(p, ra, j - JLO, a0, a1);
+            emphasise<FAM>(p, rb, j - JLO, b0, b1);
+            v[j].re = pmul(mkp(a0, b0), bc(w.x));
+            v[j].im = pmul(mkp(a1, b1), bc(w.y));
         } else {
-            v[j] = mk(0.f, 0.f);
+            v[j].re = bc(0.f);
+            v[j].im = bc(0.f);
         }
     }
 }
@@ -140,18 +153,32 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+struct FramePos { int c, t; bool ok; };
+__device__ __forceinline__ FramePos frame_pos(int f, int nf, int T) {
+    FramePos r;
+    r.ok = f < nf;
+    const int fc = r.ok ? f : (nf - 1);                     // invalid frames alias the last valid one (outputs suppressed)
+    r.c = fc / T;
+    r.t = fc - r.c * T;
+    return r;
+}
+
 // --------------------------------------------------------------------------------
 // the fused kernel
 // --------------------------------------------------------------------------------
-template <int NFFT, int FAM, int JLO, int JHI>
-__global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
+// MAXT / PF: two register budgets -- (512 threads, 128 regs, fetch at the top of the round) and
+// (384 threads, 168 regs, next pair prefetched into registers during the output stage)
+template <int NFFT, int FAM, int JLO, int JHI, int MAXT, bool PF>
+__global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
     typedef FftGeom<NFFT> G;
+    constexpr int NJ = JHI - JLO;
+    constexpr int F = G::M + 1;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    const int S = nthr >> 4;
+    const int HW = nthr >> 4;
 
-    {   // tables -> shared memory (L2-resident after the first CTA)
+    {   // tables -> shared memory, once per (persistent) CTA
         const int4* src = reinterpret_cast<const int4*>(p.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < p.blob_bytes / 16; i += nthr) dst[i] = __ldg(src + i);
@@ -161,261 +188,327 @@ __global__ void __launch_bounds__(kMaxThreads, 2) srfe_kernel(const KParams p) {
     T.tw1 = reinterpret_cast<const cpx*>(smem + p.off_tw1);
     T.twu = reinterpret_cast<const cpx*>(smem + p.off_twu);
     T.tw16 = reinterpret_cast<const cpx*>(smem + p.off_tw16);
-    const int* f_meta = reinterpret_cast<const int*>(smem + p.off_fm);
-    const float* f_w = reinterpret_cast<const float*>(smem + p.off_fw);
-    cpx* scratch_all = reinterpret_cast<cpx*>(smem + p.sm_scratch);
+    const int2* g_meta = reinterpret_cast<const int2*>(smem + p.off_gm);
+    const int* f_start = reinterpret_cast<const int*>(smem + p.off_fs);
+    const float4* f_w4 = reinterpret_cast<const float4*>(smem + p.off_fw4);
+    C2* scratch_all = reinterpret_cast<C2*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
     float* fmean = tile + p.T * p.tile_stride;              // MFCC only: [T] frame means, right after the dB tile
     __syncthreads();
 
-    const int hw = tid >> 4, l = tid & 15;
-    const unsigned hm = 0xFFFFu << (16 * (hw & 1));
-    cpx* xb = scratch_all + hw * G::SCRATCH_CPX;
-    const int clip0 = blockIdx.x * p.cpc;
-    const int ncl = min(p.cpc, p.n_clips - clip0);
-    const int nf = ncl * p.T;                               // flattened frames of this CTA
-    constexpr int F = G::M + 1;
-    const int TS = S + 1;                                   // FT tile row stride (odd)
-    float run_max = -CUDART_INF_F;
+    const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
+    C2* xb = scratch_all + hw * G::SCRATCH_C2;
 
-    RawFrame<FAM, JHI - JLO> raw;
-    int c_cur = 0, t_cur = hw;                              // (clip, frame) of flattened index f
-    while (t_cur >= p.T && c_cur < ncl) { t_cur -= p.T; ++c_cur; }
-    if (hw < nf)
-        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + c_cur) * p.clip_stride, p.start0 + t_cur * p.hop, l, raw);
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        const int clip0 = grp * p.cpc;
+        const int ncl = min(p.cpc, p.n_clips - clip0);
+        const int nf = ncl * p.T;                           // flattened frames of this group
+        const int npairs = (nf + 1) >> 1;
+        const int rounds = (npairs + HW - 1) / HW;
+        float run_max = -CUDART_INF_F;
 
-    const int rounds = (nf + S - 1) / S;
-    for (int it = 0; it < rounds; ++it) {
-        const int f = it * S + hw;
-        if (f < nf) {
-            const int c = c_cur, t = t_cur;
-            cpx v[G::V];
-            window_frame<NFFT, FAM, JLO, JHI>(p, raw, l, s_win, v);
-            fft_phase1<NFFT>(v, l, xb, T);
-            {   // prefetch the slot's next frame while this one goes through the exchange passes
-                t_cur += S;
-                while (t_cur >= p.T && c_cur < ncl) { t_cur -= p.T; ++c_cur; }
-                if (f + S < nf)
-                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + c_cur) * p.clip_stride,
-                                               p.start0 + t_cur * p.hop, l, raw);
-            }
-            __syncwarp(hm);
-            if (NFFT == 512) {
-                fft_phase2_512(l, xb, v);
-                __syncwarp(hm);
-                fft_store_z_512(l, v, xb);
-            } else {
-                fft_phase2_640(l, xb, v, T);
-                __syncwarp(hm);
-                fft_scatter2_640(l, v, xb);
-                __syncwarp(hm);
-                fft_phase3_640(l, xb, v);
-                __syncwarp(hm);
-                fft_store_z_640(l, v, xb);
-            }
-            __syncwarp(hm);
-            float pa[G::M / 32], pb[G::M / 32];
-            const float pmid = fft_untangle<NFFT>(l, xb, T, pa, pb);
+        RawFrame<FAM, NJ> rawA, rawB;
+        FramePos pA = frame_pos(2 * hw, nf, p.T), pB = frame_pos(2 * hw + 1, nf, p.T);
+        if (PF && (hw & ~1) < npairs) {
+            fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+            fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
+        }
 
-            if (FAM == FAM_SPEC) {
-                // density scaling, one-sided doubling (not DC / Nyquist), optional ln(. + eps)
-                const float s2 = 2.f * p.scale;
-                float* dst;
-                int kstride;
-                if (p.layout == SRFE_LAYOUT_TF) {
-                    dst = p.out + ((long long)(clip0 + c) * p.T + t) * F;
-                    kstride = 1;
+        for (int it = 0; it < rounds; ++it) {
+            const int q = it * HW + hw;
+            P2 pa[G::M / 32], pb[G::M / 32], pmid;
+            const bool active = (it * HW + (hw & ~1)) < npairs;
+            if (active) {                                   // warp-uniform: both half-warps of a warp run together
+                if (!PF) {
+                    pA = frame_pos(2 * q, nf, p.T);
+                    pB = frame_pos(2 * q + 1, nf, p.T);
+                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
+                }
+                const FramePos cA = pA, cB = pB;
+                C2 v[G::V];
+                window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
+                fft_phase1<NFFT>(v, l, xb, T);
+                __syncwarp();
+                if (NFFT == 512) {
+                    fft_phase2_512(l, xb, v);
+                    __syncwarp();
+                    fft_store_z_512(l, v, xb);
                 } else {
-                    dst = tile + (it & 1) * (F * TS) + hw;
-                    kstride = TS;
+                    fft_phase2_640(l, xb, v, T);
+                    __syncwarp();
+                    fft_scatter2_640(l, v, xb);
+                    __syncwarp();
+                    fft_phase3_640(l, xb, v);
+                    __syncwarp();
+                    fft_store_z_640(l, v, xb);
                 }
-#pragma unroll
-                for (int r = 0; r < G::M / 32; ++r) {
-                    const int k = l + 16 * r;
-                    float a = pa[r] * ((r == 0 && l == 0) ? p.scale : s2);
-                    float b = pb[r] * ((r == 0 && l == 0) ? p.scale : s2);
-                    if (p.take_log) { a = __logf(a + p.log_eps); b = __logf(b + p.log_eps); }
-                    dst[k * kstride] = a;
-                    dst[(G::M - k) * kstride] = b;
-                }
-                if (l == 0) {
-                    float cc = pmid * s2;
-                    if (p.take_log) cc = __logf(cc + p.log_eps);
-                    dst[(G::M / 2) * kstride] = cc;
-                }
-            } else {
-                // power -> shared (aliases the FFT scratch), then sparse triangular sums
-                float* pbuf = reinterpret_cast<float*>(xb);
-                __syncwarp(hm);
-#pragma unroll
-                for (int r = 0; r < G::M / 32; ++r) {
-                    const int k = l + 16 * r;
-                    pbuf[k] = pa[r];
-                    pbuf[G::M - k] = pb[r];
-                }
-                if (l == 0) pbuf[G::M / 2] = pmid;
-                __syncwarp(hm);
-                float* orow = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + c) * p.T + t) * p.n_filt
-                                                 : tile + t * p.tile_stride;
-                float fsum = 0.f;
-                for (int m = l; m < p.n_filt; m += 16) {
-                    const int meta = f_meta[m];
-                    const int cn = (meta >> 10) & 0xff;
-                    const float* wq = f_w + (meta >> 18);
-                    const float* pq = pbuf + (meta & 0x3ff);
-                    float acc = 0.f;
-                    for (int q = 0; q < cn; ++q) acc = fmaf(wq[q], pq[q], acc);
-                    if (FAM == FAM_FBANK) {
-                        if (acc == 0.f) acc = 2.220446049250313e-16f;              // model_fbanks_cnn.py:61
-                        orow[m] = 6.020599913279624f * __log2f(acc);               // 20 log10
-                    } else {
-                        const float db = 3.010299956639812f * __log2f(fmaxf(acc, p.amin));   // 10 log10
-                        orow[m] = db;
-                        run_max = fmaxf(run_max, db);
-                        fsum += db;
+                __syncwarp();
+                pmid = fft_untangle<NFFT>(l, xb, T, pa, pb);
+
+                if (PF) {   // prefetch the half-warp's next pair while this one goes through its output stage
+                    const int qn = q + HW;
+                    pA = frame_pos(2 * qn, nf, p.T);
+                    pB = frame_pos(2 * qn + 1, nf, p.T);
+                    if (((it + 1) * HW + (hw & ~1)) < npairs) {
+                        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+                        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
                     }
                 }
-                if (FAM == FAM_MFCC) {                       // per-frame mean dB: centre of the DCT accumulation
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) fsum += __shfl_xor_sync(hm, fsum, o);
-                    if (l == 0) fmean[t] = fsum / (float)p.n_filt;
-                }
-                __syncwarp(hm);
-            }
-        }
-        if (FAM == FAM_SPEC && p.layout == SRFE_LAYOUT_FT) {
-            // 16*S threads: thread -> (slot = tid % S, k = tid / S + 16 i); one barrier per round
-            __syncthreads();
-            const int slot = tid % S;
-            const int fs = it * S + slot;
-            if (fs < nf) {
-                const int c = fs / p.T, t = fs - c * p.T;
-                const float* src = tile + (it & 1) * (F * TS) + slot;
-                float* oc = p.out + (long long)(clip0 + c) * F * p.T + t;
-                for (int k = tid / S; k < F; k += 16) oc[(long long)k * p.T] = src[k * TS];
-            }
-        }
-    }
 
-    if (FAM == FAM_MFCC) {
-        __shared__ float s_red[kMaxThreads / 32];
+                if (FAM == FAM_SPEC) {
+                    // density scaling, one-sided doubling (not DC / Nyquist), optional ln(. + eps)
+                    const float s2 = 2.f * p.scale;
+                    if (p.layout == SRFE_LAYOUT_TF) {
+                        float* rowA = p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * F;
+                        float* rowB = p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * F;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
-        if ((tid & 31) == 0) s_red[tid >> 5] = run_max;
-        __syncthreads();
-        float gmax = s_red[0];
-        for (int i = 1; i < (nthr >> 5); ++i) gmax = fmaxf(gmax, s_red[i]);
-        const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
-        // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
-        //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
-        // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
-        // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
-        const int TC = p.T + 1;
-        float* ctile;
-        if (p.use_mma) {
-            // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels
-            float* dtab = reinterpret_cast<float*>(scratch_all);          // [nt8*8][DS], aliases the FFT scratch
-            const int DS = p.n_filt + 4;
-            ctile = dtab + p.nt8 * 8 * DS;
-            const int q4 = p.n_filt >> 2;
-            for (int idx = tid; idx < p.nt8 * 8 * q4; idx += nthr) {
-                const int row = idx / q4, c4 = idx - row * q4;
-                *reinterpret_cast<float4*>(dtab + row * DS + 4 * c4) =
-                    __ldg(reinterpret_cast<const float4*>(p.dct_kf + row * p.n_filt) + c4);
+                        for (int r = 0; r < G::M / 32; ++r) {
+                            const int k = l + 16 * r;
+                            const float sc = (r == 0 && l == 0) ? p.scale : s2;
+                            float a0 = pa[r].lo * sc, a1 = pa[r].hi * sc, b0 = pb[r].lo * sc, b1 = pb[r].hi * sc;
+                            if (p.take_log) {
+                                a0 = __logf(a0 + p.log_eps); a1 = __logf(a1 + p.log_eps);
+                                b0 = __logf(b0 + p.log_eps); b1 = __logf(b1 + p.log_eps);
+                            }
+                            if (cA.ok) { rowA[k] = a0; rowA[G::M - k] = b0; }
+                            if (cB.ok) { rowB[k] = a1; rowB[G::M - k] = b1; }
+                        }
+                        if (l == 0) {
+                            float c0 = pmid.lo * s2, c1 = pmid.hi * s2;
+                            if (p.take_log) { c0 = __logf(c0 + p.log_eps); c1 = __logf(c1 + p.log_eps); }
+                            if (cA.ok) rowA[G::M / 2] = c0;
+                            if (cB.ok) rowB[G::M / 2] = c1;
+                        }
+                    } else {
+                        // FT: keep the scaled / logged values in registers; they go through a CTA-wide
+                        // [bin][frames of this round] tile after the round's barrier (below)
+                        const float s2b = 2.f * p.scale;
+#pragma unroll
+                        for (int r = 0; r < G::M / 32; ++r) {
+                            const float sc = (r == 0 && l == 0) ? p.scale : s2b;
+                            pa[r] = pmul(pa[r], bc(sc));
+                            pb[r] = pmul(pb[r], bc(sc));
+                            if (p.take_log) {
+                                pa[r] = mkp(__logf(pa[r].lo + p.log_eps), __logf(pa[r].hi + p.log_eps));
+                                pb[r] = mkp(__logf(pb[r].lo + p.log_eps), __logf(pb[r].hi + p.log_eps));
+                            }
+                        }
+                        pmid = pmul(pmid, bc(s2b));
+                        if (p.take_log) pmid = mkp(__logf(pmid.lo + p.log_eps), __logf(pmid.hi + p.log_eps));
+                    }
+                } else {
+                    // power -> shared as (A, B) pairs (aliases the FFT scratch), then sparse triangular sums:
+                    // 16-filter groups with a uniform trip count (ELL), weights as float4 runs
+                    P2* pbuf = reinterpret_cast<P2*>(xb);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < G::M / 32; ++r) {
+                        const int k = l + 16 * r;
+                        pbuf[k] = pa[r];
+                        pbuf[G::M - k] = pb[r];
+                    }
+                    if (l == 0) pbuf[G::M / 2] = pmid;
+                    __syncwarp();
+                    float* orowA = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * p.n_filt
+                                                      : tile + cA.t * p.tile_stride;
+                    float* orowB = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * p.n_filt
+                                                      : tile + cB.t * p.tile_stride;
+                    P2 fsum = bc(0.f);
+                    for (int i = 0; i < p.n_fgroups; ++i) {
+                        const int2 gm = g_meta[i];
+                        const int m = 16 * i + l;
+                        const P2* pq = pbuf + f_start[m];
+                        const float4* wq = f_w4 + gm.x * 16 + l;
+                        P2 acc = bc(0.f);
+                        for (int q4 = 0; q4 < gm.y; ++q4) {
+                            const float4 w = wq[q4 * 16];
+                            acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
+                            acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
+                            acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
+                            acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                        }
+                        if (m < p.n_filt) {
+                            if (FAM == FAM_FBANK) {
+                                float a = acc.lo, b = acc.hi;
+                                if (a == 0.f) a = 2.220446049250313e-16f;              // model_fbanks_cnn.py:61
+                                if (b == 0.f) b = 2.220446049250313e-16f;
+                                if (cA.ok) orowA[m] = 6.020599913279624f * __log2f(a);  // 20 log10
+                                if (cB.ok) orowB[m] = 6.020599913279624f * __log2f(b);
+                            } else {
+                                const float da = 3.010299956639812f * __log2f(fmaxf(acc.lo, p.amin));   // 10 log10
+                                const float db = 3.010299956639812f * __log2f(fmaxf(acc.hi, p.amin));
+                                if (cA.ok) { orowA[m] = da; run_max = fmaxf(run_max, da); }
+                                if (cB.ok) { orowB[m] = db; run_max = fmaxf(run_max, db); }
+                                fsum = padd(fsum, mkp(da, db));
+                            }
+                        }
+                    }
+                    if (FAM == FAM_MFCC) {                   // per-frame mean dB: centre of the DCT accumulation
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) {
+                            fsum.lo += __shfl_xor_sync(0xffffffffu, fsum.lo, o);
+                            fsum.hi += __shfl_xor_sync(0xffffffffu, fsum.hi, o);
+                        }
+                        if (l == 0) {
+                            if (cA.ok) fmean[cA.t] = fsum.lo / (float)p.n_filt;
+                            if (cB.ok) fmean[cB.t] = fsum.hi / (float)p.n_filt;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
-            __syncthreads();
-            const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-            const int mtiles = (p.T + 15) >> 4;
-            for (int mt = warp; mt < mtiles; mt += (nthr >> 5)) {
-                float acc[8][4];
+            if (FAM == FAM_SPEC && p.layout == SRFE_LAYOUT_FT) {
+                // CTA-wide tile [bin][2 HW frames] aliased onto the (now idle) FFT scratch; rows of up to
+                // 2 HW consecutive frames leave as long runs along time
+                float* ft = reinterpret_cast<float*>(scratch_all);
+                const int RS = 2 * HW + 1;
+                __syncthreads();                            // every half-warp is done with its Z buffer
+                if (active) {
+                    float* col = ft + 2 * hw;
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-                const int t0 = mt * 16;
-                const int tra = min(t0 + g, p.T - 1), trb = min(t0 + g + 8, p.T - 1);
-                const float* ra = tile + tra * p.tile_stride + q;
-                const float* rb = tile + trb * p.tile_stride + q;
-                const float ca = fmaxf(fmean[tra], thr), cb = fmaxf(fmean[trb], thr);
-                for (int ks = 0; ks < (p.n_filt >> 3); ++ks) {
-                    uint32_t ah[4], al[4];
-                    split_tf32(fmaxf(ra[8 * ks], thr) - ca, ah[0], al[0]);
-                    split_tf32(fmaxf(rb[8 * ks], thr) - cb, ah[1], al[1]);
-                    split_tf32(fmaxf(ra[8 * ks + 4], thr) - ca, ah[2], al[2]);
-                    split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
+                    for (int r = 0; r < G::M / 32; ++r) {
+                        const int k = l + 16 * r;
+                        col[k * RS] = pa[r].lo;            col[k * RS + 1] = pa[r].hi;
+                        col[(G::M - k) * RS] = pb[r].lo;   col[(G::M - k) * RS + 1] = pb[r].hi;
+                    }
+                    if (l == 0) { col[(G::M / 2) * RS] = pmid.lo; col[(G::M / 2) * RS + 1] = pmid.hi; }
+                }
+                __syncthreads();
+                const int f0 = 2 * it * HW;
+                for (int cb = 0; cb < 2 * HW; cb += 32) {
+                    const FramePos po = frame_pos(f0 + cb + lane, nf, p.T);
+                    if (cb + lane < 2 * HW && po.ok) {
+                        float* oc = p.out + (long long)(clip0 + po.c) * F * p.T + po.t;
+                        const float* src = ft + cb + lane;
+                        for (int k = tid >> 5; k < F; k += (nthr >> 5)) oc[(long long)k * p.T] = src[k * RS];
+                    }
+                }
+                __syncthreads();                            // the tile is scratch again in the next round
+            }
+        }
+
+        if (FAM == FAM_MFCC) {
+            __shared__ float s_red[MAXT / 32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+            if ((tid & 31) == 0) s_red[tid >> 5] = run_max;
+            __syncthreads();
+            float gmax = s_red[0];
+            for (int i = 1; i < (nthr >> 5); ++i) gmax = fmaxf(gmax, s_red[i]);
+            const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
+            // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
+            //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
+            // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
+            // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
+            const int TC = p.T + 1;
+            float* ctile;
+            if (p.use_mma) {
+                // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels
+                float* dtab = reinterpret_cast<float*>(scratch_all);          // [nt8*8][DS], aliases the FFT scratch
+                const int DS = p.n_filt + 4;
+                ctile = dtab + p.nt8 * 8 * DS;
+                const int q4n = p.n_filt >> 2;
+                for (int idx = tid; idx < p.nt8 * 8 * q4n; idx += nthr) {
+                    const int row = idx / q4n, c4 = idx - row * q4n;
+                    *reinterpret_cast<float4*>(dtab + row * DS + 4 * c4) =
+                        __ldg(reinterpret_cast<const float4*>(p.dct_kf + row * p.n_filt) + c4);
+                }
+                __syncthreads();
+                const int warp = tid >> 5, g = lane >> 2, qq = lane & 3;
+                const int mtiles = (p.T + 15) >> 4;
+                for (int mt = warp; mt < mtiles; mt += (nthr >> 5)) {
+                    float acc[8][4];
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+                    const int t0 = mt * 16;
+                    const int tra = min(t0 + g, p.T - 1), trb = min(t0 + g + 8, p.T - 1);
+                    const float* ra = tile + tra * p.tile_stride + qq;
+                    const float* rb = tile + trb * p.tile_stride + qq;
+                    const float ca = fmaxf(fmean[tra], thr), cb = fmaxf(fmean[trb], thr);
+                    for (int ks = 0; ks < (p.n_filt >> 3); ++ks) {
+                        uint32_t ah[4], al[4];
+                        split_tf32(fmaxf(ra[8 * ks], thr) - ca, ah[0], al[0]);
+                        split_tf32(fmaxf(rb[8 * ks], thr) - cb, ah[1], al[1]);
+                        split_tf32(fmaxf(ra[8 * ks + 4], thr) - ca, ah[2], al[2]);
+                        split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            if (nt < p.nt8) {
+                                const float* dr = dtab + (nt * 8 + g) * DS + 8 * ks + qq;
+                                uint32_t bh0, bl0, bh1, bl1;
+                                split_tf32(dr[0], bh0, bl0);
+                                split_tf32(dr[4], bh1, bl1);
+                                mma_tf32(acc[nt], al, bh0, bh1);
+                                mma_tf32(acc[nt], ah, bl0, bl1);
+                                mma_tf32(acc[nt], ah, bh0, bh1);
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         if (nt < p.nt8) {
-                            const float* dr = dtab + (nt * 8 + g) * DS + 8 * ks + q;
-                            uint32_t bh0, bl0, bh1, bl1;
-                            split_tf32(dr[0], bh0, bl0);
-                            split_tf32(dr[4], bh1, bl1);
-                            mma_tf32(acc[nt], al, bh0, bh1);
-                            mma_tf32(acc[nt], ah, bl0, bl1);
-                            mma_tf32(acc[nt], ah, bh0, bh1);
+                            const int k = nt * 8 + 2 * qq, ta = t0 + g, tb = t0 + g + 8;
+                            if (k == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
+                            if (k < p.n_mfcc) {
+                                if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
+                                if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
+                            }
+                            if (k + 1 < p.n_mfcc) {
+                                if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
+                                if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
+                            }
                         }
                     }
                 }
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    if (nt < p.nt8) {
-                        const int k = nt * 8 + 2 * q, ta = t0 + g, tb = t0 + g + 8;
-                        if (k == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
-                        if (k < p.n_mfcc) {
-                            if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
-                            if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
-                        }
-                        if (k + 1 < p.n_mfcc) {
-                            if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
-                            if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
-                        }
-                    }
-                }
-            }
-        } else {
-            ctile = reinterpret_cast<float*>(scratch_all);
-            const int kq_n = p.n_mfcc_pad / 4;
-            for (int task = tid; task < p.T * kq_n; task += nthr) {
-                const int t = task % p.T, kq = task / p.T;
-                const float* row = tile + t * p.tile_stride;
-                const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float ct = fmaxf(fmean[t], thr);
+            } else {
+                ctile = reinterpret_cast<float*>(scratch_all);
+                const int kq_n = p.n_mfcc_pad / 4;
+                for (int task = tid; task < p.T * kq_n; task += nthr) {
+                    const int t = task % p.T, kq = task / p.T;
+                    const float* row = tile + t * p.tile_stride;
+                    const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float ct = fmaxf(fmean[t], thr);
 #pragma unroll 4
-                for (int f = 0; f < p.n_filt; ++f) {
-                    const float d = fmaxf(row[f], thr) - ct;
-                    const float4 w = __ldg(dcol + f * kq_n);
-                    acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
-                    acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+                    for (int f = 0; f < p.n_filt; ++f) {
+                        const float d = fmaxf(row[f], thr) - ct;
+                        const float4 w = __ldg(dcol + f * kq_n);
+                        acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
+                        acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+                    }
+                    const int k0 = 4 * kq;
+                    if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
+                    ctile[(k0 + 0) * TC + t] = acc.x;
+                    if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
+                    if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
+                    if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
                 }
-                const int k0 = 4 * kq;
-                if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
-                ctile[(k0 + 0) * TC + t] = acc.x;
-                if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
-                if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
-                if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
-            }
-        }
-        __syncthreads();
-        // np.gradient along time (unit spacing, edge_order 1), applied n_deltas times
-        for (int d = 1; d <= p.n_deltas; ++d) {
-            const float* src = ctile + (d - 1) * p.n_mfcc * TC;
-            float* dst = ctile + d * p.n_mfcc * TC;
-            for (int idx = tid; idx < p.n_mfcc * p.T; idx += nthr) {
-                const int k = idx / p.T, t = idx % p.T;
-                const float* s = src + k * TC;
-                float g;
-                if (t == 0) g = s[1] - s[0];
-                else if (t == p.T - 1) g = s[t] - s[t - 1];
-                else g = 0.5f * (s[t + 1] - s[t - 1]);
-                dst[k * TC + t] = g;
             }
             __syncthreads();
-        }
-        const int R = (1 + p.n_deltas) * p.n_mfcc;
-        float* oc = p.out + (long long)clip0 * R * p.T;
-        if (p.layout == SRFE_LAYOUT_FT) {
-            for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx / p.T) * TC + idx % p.T];
-        } else {
-            for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx % R) * TC + idx / R];
+            // np.gradient along time (unit spacing, edge_order 1), applied n_deltas times
+            for (int d = 1; d <= p.n_deltas; ++d) {
+                const float* src = ctile + (d - 1) * p.n_mfcc * TC;
+                float* dst = ctile + d * p.n_mfcc * TC;
+                for (int idx = tid; idx < p.n_mfcc * p.T; idx += nthr) {
+                    const int k = idx / p.T, t = idx % p.T;
+                    const float* s = src + k * TC;
+                    float g;
+                    if (t == 0) g = s[1] - s[0];
+                    else if (t == p.T - 1) g = s[t] - s[t - 1];
+                    else g = 0.5f * (s[t + 1] - s[t - 1]);
+                    dst[k * TC + t] = g;
+                }
+                __syncthreads();
+            }
+            const int R = (1 + p.n_deltas) * p.n_mfcc;
+            float* oc = p.out + (long long)clip0 * R * p.T;
+            if (p.layout == SRFE_LAYOUT_FT) {
+                for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx / p.T) * TC + idx % p.T];
+            } else {
+                for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx % R) * TC + idx / R];
+            }
+            __syncthreads();                                // scratch / tile are reused by the next clip
         }
     }
 }

@@ -168,6 +168,33 @@ void to_sparse(const std::vector<double>& dense, int n_filters, int n_bins, doub
     }
 }
 
+void to_ell(const SparseBank& sb, EllBank& out) {
+    const int n = (int)sb.start.size();
+    out.groups = (n + 15) / 16;
+    out.gmeta.assign(2 * out.groups, 0);
+    out.start.assign(16 * out.groups, 0);
+    out.w4.clear();
+    out.max_reach = 0;
+    int off4 = 0;
+    for (int g = 0; g < out.groups; ++g) {
+        int cmax = 0;
+        for (int l = 0; l < 16; ++l) { const int m = 16 * g + l; if (m < n && sb.count[m] > cmax) cmax = sb.count[m]; }
+        const int n4 = (cmax + 3) / 4;
+        out.gmeta[2 * g] = off4;
+        out.gmeta[2 * g + 1] = n4;
+        out.w4.resize((size_t)(off4 + n4) * 16 * 4, 0.f);
+        for (int l = 0; l < 16; ++l) {
+            const int m = 16 * g + l;
+            if (m >= n) continue;
+            out.start[m] = sb.start[m];
+            for (int q = 0; q < sb.count[m]; ++q)
+                out.w4[((size_t)(off4 + q / 4) * 16 + l) * 4 + (q & 3)] = sb.weight[sb.offset[m] + q];
+            if (sb.start[m] + 4 * n4 > out.max_reach) out.max_reach = sb.start[m] + 4 * n4;
+        }
+        off4 += n4;
+    }
+}
+
 void fft_twiddles(int n_fft, std::vector<F2>& tw1, std::vector<F2>& twu, std::vector<F2>& tw16) {
     const int M = n_fft / 2, V = M / 16;
     tw1.resize(M);

@@ -41,6 +41,17 @@ struct SparseBank {
 };
 void to_sparse(const std::vector<double>& dense, int n_filters, int n_bins, double scale, SparseBank& out);
 
+// --- ELL form for the kernels: filters in groups of 16 (one per lane), every group padded to a common
+//     multiple-of-4 run length so the inner loop has a uniform trip count and reads float4 weights
+struct EllBank {
+    std::vector<int32_t> gmeta;      // per group: {offset into w4 (float4 units, /16 lanes), n4 = run length / 4}
+    std::vector<int32_t> start;      // per filter (padded to 16 * groups): first bin
+    std::vector<float> w4;           // [(offset + q4) * 16 + lane] float4 = 4 consecutive weights
+    int groups = 0;
+    int max_reach = 0;               // max over filters of start + 4 * n4 (bins read, incl. padding)
+};
+void to_ell(const SparseBank& sb, EllBank& out);
+
 // --- FFT twiddles (see srfe_fft.cuh) ---------------------------------------------------
 void fft_twiddles(int n_fft, std::vector<F2>& tw1, std::vector<F2>& twu, std::vector<F2>& tw16);
 

@@ -1,11 +1,12 @@
-// fft_emu.cpp -- CPU lane-by-lane emulation of the half-warp FFT pipeline of
+// fft_emu.cpp -- CPU lane-by-lane emulation of the packed half-warp FFT pipeline of
 // speechrecognitionproject_b200/csrc/srfe_fft.cuh (TEST INFRASTRUCTURE).
 //
-// The device code separates its phases with warp syncs; here every phase is run
-// for lanes 0..15 in a loop, against a plain array standing in for the shared
-// memory scratch.  Same templates, same index arithmetic, same tables -- so a
-// wrong permutation or twiddle shows up in `pytest -m "not gpu"` instead of
-// costing a GPU round trip.  Not part of the product; never used as a fallback.
+// The device code separates its phases with warp syncs; here every phase is run for
+// lanes 0..15 in a loop, against a plain array standing in for the shared-memory
+// scratch.  Same templates, same index arithmetic, same tables (the f32x2 PTX ops have a
+// plain C++ body on the host) -- so a wrong permutation or twiddle shows up in
+// `pytest -m "not gpu"` instead of costing a GPU round trip.  Not part of the product;
+// never used as a fallback.
 #include <cstring>
 #include <vector>
 
@@ -15,7 +16,7 @@
 using namespace srfe;
 
 template <int NFFT>
-static void run(const float* xw, float* p) {
+static void run(const float* xa, const float* xb, float* pa_out, float* pb_out) {
     typedef FftGeom<NFFT> G;
     std::vector<F2> tw1, twu, tw16;
     fft_twiddles(NFFT, tw1, twu, tw16);
@@ -24,13 +25,13 @@ static void run(const float* xw, float* p) {
     T.twu = reinterpret_cast<const cpx*>(twu.data());
     T.tw16 = reinterpret_cast<const cpx*>(tw16.data());
 
-    std::vector<cpx> scratch(G::SCRATCH_CPX);
-    cpx v[16][G::V];
-    // phase 0: lane l takes z[l + 16 j] = (xw[2m], xw[2m+1])
+    std::vector<C2> scratch(G::SCRATCH_C2);
+    static C2 v[16][G::V];
     for (int l = 0; l < 16; ++l)
         for (int j = 0; j < G::V; ++j) {
             const int m = l + 16 * j;
-            v[l][j] = mk(xw[2 * m], xw[2 * m + 1]);
+            v[l][j].re = mkp(xa[2 * m], xb[2 * m]);
+            v[l][j].im = mkp(xa[2 * m + 1], xb[2 * m + 1]);
         }
     for (int l = 0; l < 16; ++l) fft_phase1<NFFT>(v[l], l, scratch.data(), T);
     if (NFFT == 512) {
@@ -43,31 +44,36 @@ static void run(const float* xw, float* p) {
         for (int l = 0; l < 16; ++l) fft_store_z_640(l, v[l], scratch.data());
     }
     for (int l = 0; l < 16; ++l) {
-        float pa[G::M / 32], pb[G::M / 32];
-        const float pmid = fft_untangle<NFFT>(l, scratch.data(), T, pa, pb);
+        P2 pa[G::M / 32], pb[G::M / 32];
+        const P2 pmid = fft_untangle<NFFT>(l, scratch.data(), T, pa, pb);
         for (int r = 0; r < G::M / 32; ++r) {
             const int k = l + 16 * r;
-            p[k] = 0.25f * pa[r];
-            p[G::M - k] = 0.25f * pb[r];
+            pa_out[k] = 0.25f * pa[r].lo;           pb_out[k] = 0.25f * pa[r].hi;
+            pa_out[G::M - k] = 0.25f * pb[r].lo;    pb_out[G::M - k] = 0.25f * pb[r].hi;
         }
-        if (l == 0) p[G::M / 2] = 0.25f * pmid;
+        if (l == 0) { pa_out[G::M / 2] = 0.25f * pmid.lo; pb_out[G::M / 2] = 0.25f * pmid.hi; }
     }
 }
 
-extern "C" int emu_power(int nfft, const float* xw, float* p) {
-    if (nfft == 512) { run<512>(xw, p); return 0; }
-    if (nfft == 640) { run<640>(xw, p); return 0; }
+// power spectra |rfft(x)|^2 of two frames processed as one packed pair
+extern "C" int emu_power2(int nfft, const float* xa, const float* xb, float* pa, float* pb) {
+    if (nfft == 512) { run<512>(xa, xb, pa, pb); return 0; }
+    if (nfft == 640) { run<640>(xa, xb, pa, pb); return 0; }
     return -1;
 }
 
-extern "C" int emu_dft(int n, const float* in_ri, float* out_ri) {
-    cpx v[20];
-    for (int i = 0; i < n; ++i) v[i] = mk(in_ri[2 * i], in_ri[2 * i + 1]);
+// complex DFT codelets on two packed inputs (interleaved re/im arrays)
+extern "C" int emu_dft2(int n, const float* a_ri, const float* b_ri, float* oa_ri, float* ob_ri) {
+    C2 v[20];
+    for (int i = 0; i < n; ++i) { v[i].re = mkp(a_ri[2 * i], b_ri[2 * i]); v[i].im = mkp(a_ri[2 * i + 1], b_ri[2 * i + 1]); }
     if (n == 4) dft4(v[0], v[1], v[2], v[3]);
     else if (n == 5) dft5(v[0], v[1], v[2], v[3], v[4]);
     else if (n == 16) dft16(v);
     else if (n == 20) dft20(v);
     else return -1;
-    for (int i = 0; i < n; ++i) { out_ri[2 * i] = v[i].x; out_ri[2 * i + 1] = v[i].y; }
+    for (int i = 0; i < n; ++i) {
+        oa_ri[2 * i] = v[i].re.lo; oa_ri[2 * i + 1] = v[i].im.lo;
+        ob_ri[2 * i] = v[i].re.hi; ob_ri[2 * i + 1] = v[i].im.hi;
+    }
     return 0;
 }
