@@ -1,0 +1,43 @@
+"""Attribute an `ncu --page source --csv` SASS dump to CUDA source lines using nvdisasm -g line info.
+usage: ncu_lines.py <src.csv> <libsrfe.so> [topN]"""
+import csv, sys, re, subprocess, collections, os, tempfile, glob
+src_csv, so = sys.argv[1], sys.argv[2]
+topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+rows = list(csv.reader(open(src_csv)))
+kname = rows[0][1]
+m = re.search(r"srfe_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d)>", kname)
+mangled = "srfe_kernelILi%sELi%sELi%sELi%sELi%sELb%sEE" % m.groups()
+hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+hdr = rows[hdr_i]; body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+ci = {h: i for i, h in enumerate(hdr)}
+d = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
+cub = [f for f in glob.glob(d + "/*.cubin") if "tables" not in f][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
+lines, cur, infn = [], ("?", 0), False
+for ln in dis:
+    if ln.startswith(".text."):
+        infn = mangled in ln
+        continue
+    if not infn: continue
+    mm = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+    if mm: cur = (os.path.basename(mm.group(1)), int(mm.group(2))); continue
+    if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln): lines.append(cur)
+assert len(lines) >= len(body), (len(lines), len(body))
+agg = collections.defaultdict(lambda: [0.0, 0.0])
+tot_i = tot_s = 0.0
+for r, loc in zip(body, lines):
+    i = float(r[ci["Instructions Executed"]] or 0); s = float(r[ci["# Samples"]] or 0)
+    agg[loc][0] += i; agg[loc][1] += s; tot_i += i; tot_s += s
+srcs = {}
+def text(loc):
+    f, n = loc
+    for base in ("speechrecognitionproject_b200/csrc/", ""):
+        p = base + f
+        if os.path.exists(p):
+            if p not in srcs: srcs[p] = open(p).read().splitlines()
+            return srcs[p][n - 1].strip()[:90] if n - 1 < len(srcs[p]) else ""
+    return ""
+print(f"{kname}\ninstr {tot_i:.0f} samples {tot_s:.0f}")
+for loc, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+    print(f"{100*i/tot_i:5.1f}%i {100*s/max(tot_s,1):5.1f}%s  {loc[0]}:{loc[1]:<4d} {text(loc)}")

@@ -119,6 +119,8 @@ static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_ff
     kp.off_fw4 = bb.add(ell.w4.data(), ell.w4.size() * 4);
     kp.n_filt = (int)sb.start.size();
     kp.n_fgroups = ell.groups;
+    kp.ell_n4max = 0;
+    for (int g = 0; g < ell.groups; ++g) kp.ell_n4max = std::max(kp.ell_n4max, ell.gmeta[2 * g + 1]);
     return SRFE_OK;
 }
 
@@ -263,54 +265,86 @@ static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, bo
     return launch_k<NFFT, FAM, JLO, JHI, 512, false>(kp, grid, threads, smem_bytes, st);
 }
 
-struct Config { int warps, ctas, cpc, smem, scratch, tile; };
+struct Config { int warps, ctas, cpc, smem, scratch, tile, dtab_off, ctile_off, dtab_resident; };
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// shared memory of a CTA with `warps` warps; returns total bytes, fills scratch/tile sizes
-static int smem_for(const Entry* e, const KParams& kp, int warps, int* scratch_out, int* tile_out) {
+// Shared-memory plan of a CTA with `warps` warps and up to `budget` bytes:
+//   [tables][FFT scratch][dB tile + dummy row + frame means][resident DCT table?]
+// The MFCC epilogue reuses the FFT scratch for the coefficient tile (and, when the pre-split DCT table
+// is not resident, for that table too); delta rows may spill into the (dead) dB tile.
+static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, Config* c) {
     const int hw = 2 * warps;
+    const int blob = align16(e->blob_smem);
     int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 16;
-    int tile = 0;
+    int tile = 0, dtab = 0;
+    c->dtab_resident = 0;
+    c->dtab_off = c->ctile_off = blob;
     if (e->family == FAM_MFCC) {
-        tile = kp.T * kp.tile_stride * 4 + kp.T * 4;                 // dB tile + per-frame means
-        const int TC = kp.T + 1;
-        // epilogue reuses the FFT scratch: [DCT table (tensor-core path)][static coefficients] must not
-        // reach into the dB tile; the delta rows may (the tile is dead by then)
-        const int dtab = kp.use_mma ? kp.nt8 * 8 * (kp.n_filt + 4) * 4 : 0;
-        if (dtab + kp.n_mfcc * TC * 4 > scratch) scratch = align16(dtab + kp.n_mfcc * TC * 4);
-        if (dtab + (1 + kp.n_deltas) * kp.n_mfcc * TC * 4 > scratch + align16(tile)) return -1;
+        tile = align16((kp.T + 1) * kp.tile_stride * 4 + kp.T * 4);
+        const int TC = kp.T + 1 + (kp.T & 1);
+        const int cstat = align16(kp.n_mfcc * TC * 4), call = (1 + kp.n_deltas) * kp.n_mfcc * TC * 4;
+        dtab = kp.use_mma ? kp.nt8 * 8 * ((kp.n_filt / 8) * 4 + 4) * 16 : 0;   // float4 {hi pair, lo pair} per (row, k-step, q)
+        if (dtab && env_int("SRFE_DTAB_RESIDENT", 1) && blob + std::max(scratch, cstat) + tile + dtab <= budget &&
+            call <= std::max(scratch, cstat) + tile) {
+            c->dtab_resident = 1;                                    // own region after the tile
+            scratch = std::max(scratch, cstat);
+            c->dtab_off = blob + scratch + tile;
+            c->ctile_off = blob;
+        } else {
+            if (dtab + cstat > scratch) scratch = align16(dtab + cstat);
+            if (dtab + call > scratch + tile) return -1;
+            c->dtab_off = blob;
+            c->ctile_off = blob + dtab;
+            dtab = 0;
+        }
     }
-    *scratch_out = scratch;
-    *tile_out = align16(tile);
-    return align16(e->blob_smem) + scratch + align16(tile);
+    c->scratch = scratch;
+    c->tile = tile;
+    c->smem = blob + scratch + tile + dtab;
+    return c->smem;
+}
+
+// K split of the tensor-core DCT: 2 when that still gives every warp at most one (M-tile, K-half) task
+// (2 partial sums added with shared-memory atomics: commutative, so the result stays deterministic)
+static int dct_ksplit_for(const KParams& kp, int warps) {
+    const int mtiles = (kp.T + 15) / 16, ksteps = kp.n_filt / 8;
+    return (ksteps % 2 == 0 && mtiles * 2 <= warps) ? 2 : 1;
 }
 
 // Warps per CTA, CTAs per SM and clips per group: fill whole rounds of 4*warps frames, keep as many
 // warps resident as the shared-memory budget allows, prefer two CTAs per SM (their phases overlap).
 static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Config* out) {
     double best = -1.0;
-    Config bc{0, 0, 1, 0, 0, 0};
-    const int cpc_max = (e->family == FAM_MFCC) ? 1 : 8;
+    Config bc{0, 0, 1, 0, 0, 0, 0, 0, 0};
+    int cpc_max = (e->family == FAM_MFCC) ? 1 : 8;
+    if (8.0 * kp.T * kp.T >= 4294967296.0) cpc_max = 1;              // magic division range (frame_pos)
     const int per_sm = 228 * 1024;                                   // B200: 228 KB per SM, 1 KB reserved per CTA
     for (int ctas = 1; ctas <= 2; ++ctas) {
         const int budget = std::min(di.smem_optin, per_sm / ctas - 1024);
         for (int warps = (ctas == 1 ? 8 : 4); warps <= (ctas == 1 ? 16 : 8); ++warps) {
-            int scratch = 0, tile = 0;
-            const int smem = smem_for(e, kp, warps, &scratch, &tile);
+            Config pl{};
+            const int smem = smem_plan(e, kp, warps, budget, &pl);
             if (smem < 0 || smem > budget) continue;
             for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
                 if (cpc > 1 && cpc > kp.n_clips) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
+                // measured on B200 (scripts/tune.py): two co-resident CTAs overlap their phases and beat one
+                // larger CTA with more warps; the MFCC epilogue wants every warp to own exactly one DCT task
                 double score = (double)nf / (double)(rounds * per_round);
-                score *= 0.55 + 0.45 * std::min(16, ctas * warps) / 16.0;
-                if (ctas == 1) score *= 0.94;
+                score *= 0.70 + 0.30 * std::min(16, ctas * warps) / 16.0;
+                if (ctas == 1) score *= 0.80;
                 score *= 1.0 - 0.004 * (cpc - 1);
-                if (score > best + 1e-9) { best = score; bc = Config{warps, ctas, cpc, smem, scratch, tile}; }
+                if (e->family == FAM_MFCC && kp.use_mma) {
+                    const int tasks = ((kp.T + 15) / 16) * dct_ksplit_for(kp, warps);
+                    const int waves = (tasks + warps - 1) / warps;
+                    score *= 0.80 + 0.20 * (double)tasks / (double)(waves * warps);
+                }
+                if (score > best + 1e-9) { best = score; bc = pl; bc.warps = warps; bc.ctas = ctas; bc.cpc = cpc; }
             }
         }
     }
@@ -318,11 +352,13 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
     // developer overrides (tuning only)
     const int ow = env_int("SRFE_WARPS", 0), oc = env_int("SRFE_CTAS", 0), op = env_int("SRFE_CPC", 0);
     if (ow > 0 || oc > 0 || op > 0) {
-        if (ow > 0) bc.warps = std::min(16, std::max(1, ow));
-        if (oc > 0) bc.ctas = std::min(8, std::max(1, oc));
-        if (op > 0 && e->family != FAM_MFCC) bc.cpc = op;
-        bc.smem = smem_for(e, kp, bc.warps, &bc.scratch, &bc.tile);
-        if (bc.smem < 0 || bc.smem > di.smem_optin) return fail(SRFE_ERR_TOO_LARGE, "SRFE_WARPS override does not fit in shared memory");
+        const int w_ = ow > 0 ? std::min(16, std::max(1, ow)) : bc.warps;
+        const int c_ = oc > 0 ? std::min(8, std::max(1, oc)) : bc.ctas;
+        const int p_ = (op > 0 && cpc_max > 1) ? op : bc.cpc;
+        const int budget = std::min(di.smem_optin, per_sm / c_ - 1024);
+        const int smem = smem_plan(e, kp, w_, budget, &bc);
+        bc.warps = w_; bc.ctas = c_; bc.cpc = p_;
+        if (smem < 0 || smem > budget) return fail(SRFE_ERR_TOO_LARGE, "SRFE_WARPS / SRFE_CTAS override does not fit in shared memory");
     }
     *out = bc;
     return SRFE_OK;
@@ -341,6 +377,12 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
     kp.n_groups = (kp.n_clips + cfg.cpc - 1) / cfg.cpc;
     kp.sm_scratch = align16(e->blob_smem);
     kp.sm_tile = kp.sm_scratch + cfg.scratch;
+    kp.sm_dtab = cfg.dtab_off;
+    kp.sm_ctile = cfg.ctile_off;
+    kp.dtab_resident = cfg.dtab_resident;
+    kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
+    kp.dct_ksplit = 1;
+    if (e->family == FAM_MFCC && kp.use_mma) kp.dct_ksplit = dct_ksplit_for(kp, cfg.warps);   // spread the DCT over the warps
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
     // window extent in units of 32 samples; known extents get a specialised instantiation

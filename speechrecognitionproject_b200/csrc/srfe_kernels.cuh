@@ -43,6 +43,10 @@ struct KParams {
     int n_clips, n_samples;
     int T, hop, start0;
     int cpc, n_groups;                 // clips per group, number of groups
+    unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
+    int ell_n4max;                     // max float4 steps of any 16-filter group (<= 4: unrolled path)
+    int sm_ctile, dct_ksplit;          // coefficient tile offset; K split of the DCT over warps (1, 2 or 4)
+    int sm_dtab, dtab_resident;        // tensor-core DCT: pre-split (hi, lo) table, loaded once per CTA when it fits
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
     int blob_bytes;                    // multiple of 16
     int off_win, off_tw1, off_twu, off_tw16;
@@ -130,8 +134,8 @@ __device__ __forceinline__ void window_pair(const KParams& p, const RawFrame<FAM
             float a0, a1, b0, b1;
             emphasise<FAM>(p, ra, j - JLO, a0, a1);
             emphasise<FAM>(p, rb, j - JLO, b0, b1);
-            v[j].re = pmul(mkp(a0, b0), bc(w.x));
-            v[j].im = pmul(mkp(a1, b1), bc(w.y));
+            v[j].re = mkp(a0 * w.x, b0 * w.x);           // scalar FMULs land directly in the pair registers
+            v[j].im = mkp(a1 * w.y, b1 * w.y);           // (a packed multiply would need 2 MOVs to form its operand)
         } else {
             v[j].re = bc(0.f);
             v[j].im = bc(0.f);
@@ -153,14 +157,34 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+struct KParams;
+// DCT-II rows -> shared memory, pre-split into TF32 (hi, lo) pairs for the 3xTF32 products
+// layout: float4 {hi(f), hi(f+4), lo(f), lo(f+4)} per (row, k-step, q), f = 8 ks + q: exactly the B fragments of
+// mma.m16n8k8 for lane (g = row % 8, q); row stride (K/8)*4 + 4 float4 keeps the LDS.128 conflict-free
+__device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int warp, int nwarps, int lane);
+
 struct FramePos { int c, t; bool ok; };
-__device__ __forceinline__ FramePos frame_pos(int f, int nf, int T) {
+// flattened frame -> (clip in group, frame); division by T through a host-computed magic multiplier
+// (exact for f * T < 2^32); single-clip groups (MFCC) skip it altogether
+__device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned magic, int cpc) {
     FramePos r;
     r.ok = f < nf;
     const int fc = r.ok ? f : (nf - 1);                     // invalid frames alias the last valid one (outputs suppressed)
-    r.c = fc / T;
+    r.c = (cpc == 1) ? 0 : (int)__umulhi((unsigned)fc, magic);
     r.t = fc - r.c * T;
     return r;
+}
+
+__device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int warp, int nwarps, int lane) {
+    const int ksn = p.n_filt >> 3, RS4 = ksn * 4 + 4;
+    for (int row = warp; row < p.nt8 * 8; row += nwarps)
+        for (int e = lane; e < ksn * 4; e += 32) {
+            const int ks = e >> 2, q = e & 3;
+            uint32_t h0, l0, h1, l1;
+            split_tf32(__ldg(p.dct_kf + row * p.n_filt + 8 * ks + q), h0, l0);
+            split_tf32(__ldg(p.dct_kf + row * p.n_filt + 8 * ks + q + 4), h1, l1);
+            dtab[row * RS4 + e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+        }
 }
 
 // --------------------------------------------------------------------------------
@@ -193,7 +217,9 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
     const float4* f_w4 = reinterpret_cast<const float4*>(smem + p.off_fw4);
     C2* scratch_all = reinterpret_cast<C2*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
-    float* fmean = tile + p.T * p.tile_stride;              // MFCC only: [T] frame means, right after the dB tile
+    float* fmean = tile + (p.T + 1) * p.tile_stride;        // MFCC only: [T] frame means, after the dB tile (+1 dummy row)
+    if (FAM == FAM_MFCC && p.use_mma && p.dtab_resident)
+        load_dtab(p, reinterpret_cast<float4*>(smem + p.sm_dtab), tid >> 5, nthr >> 5, tid & 31);
     __syncthreads();
 
     const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
@@ -208,7 +234,7 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
         float run_max = -CUDART_INF_F;
 
         RawFrame<FAM, NJ> rawA, rawB;
-        FramePos pA = frame_pos(2 * hw, nf, p.T), pB = frame_pos(2 * hw + 1, nf, p.T);
+        FramePos pA = frame_pos(2 * hw, nf, p.T, p.t_magic, p.cpc), pB = frame_pos(2 * hw + 1, nf, p.T, p.t_magic, p.cpc);
         if (PF && (hw & ~1) < npairs) {
             fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
             fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
@@ -220,8 +246,8 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
             const bool active = (it * HW + (hw & ~1)) < npairs;
             if (active) {                                   // warp-uniform: both half-warps of a warp run together
                 if (!PF) {
-                    pA = frame_pos(2 * q, nf, p.T);
-                    pB = frame_pos(2 * q + 1, nf, p.T);
+                    pA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc);
+                    pB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
                     fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
                     fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
                 }
@@ -248,8 +274,8 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
 
                 if (PF) {   // prefetch the half-warp's next pair while this one goes through its output stage
                     const int qn = q + HW;
-                    pA = frame_pos(2 * qn, nf, p.T);
-                    pB = frame_pos(2 * qn + 1, nf, p.T);
+                    pA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc);
+                    pB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
                     if (((it + 1) * HW + (hw & ~1)) < npairs) {
                         fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
                         fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
@@ -311,9 +337,9 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                     if (l == 0) pbuf[G::M / 2] = pmid;
                     __syncwarp();
                     float* orowA = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * p.n_filt
-                                                      : tile + cA.t * p.tile_stride;
+                                                      : tile + (cA.ok ? cA.t : p.T) * p.tile_stride;
                     float* orowB = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * p.n_filt
-                                                      : tile + cB.t * p.tile_stride;
+                                                      : tile + (cB.ok ? cB.t : p.T) * p.tile_stride;
                     P2 fsum = bc(0.f);
                     for (int i = 0; i < p.n_fgroups; ++i) {
                         const int2 gm = g_meta[i];
@@ -321,12 +347,25 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                         const P2* pq = pbuf + f_start[m];
                         const float4* wq = f_w4 + gm.x * 16 + l;
                         P2 acc = bc(0.f);
-                        for (int q4 = 0; q4 < gm.y; ++q4) {
-                            const float4 w = wq[q4 * 16];
-                            acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
-                            acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
-                            acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
-                            acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                        if (p.ell_n4max <= 4) {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                if (q4 < gm.y) {            // uniform over the warp
+                                    const float4 w = wq[q4 * 16];
+                                    acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
+                                    acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
+                                    acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
+                                    acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                                }
+                            }
+                        } else {
+                            for (int q4 = 0; q4 < gm.y; ++q4) {
+                                const float4 w = wq[q4 * 16];
+                                acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
+                                acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
+                                acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
+                                acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                            }
                         }
                         if (m < p.n_filt) {
                             if (FAM == FAM_FBANK) {
@@ -338,8 +377,9 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                             } else {
                                 const float da = 3.010299956639812f * __log2f(fmaxf(acc.lo, p.amin));   // 10 log10
                                 const float db = 3.010299956639812f * __log2f(fmaxf(acc.hi, p.amin));
-                                if (cA.ok) { orowA[m] = da; run_max = fmaxf(run_max, da); }
-                                if (cB.ok) { orowB[m] = db; run_max = fmaxf(run_max, db); }
+                                orowA[m] = da;                  // invalid frames go to the dummy row T
+                                orowB[m] = db;
+                                run_max = fmaxf(run_max, fmaxf(cA.ok ? da : -CUDART_INF_F, cB.ok ? db : -CUDART_INF_F));
                                 fsum = padd(fsum, mkp(da, db));
                             }
                         }
@@ -377,7 +417,7 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                 __syncthreads();
                 const int f0 = 2 * it * HW;
                 for (int cb = 0; cb < 2 * HW; cb += 32) {
-                    const FramePos po = frame_pos(f0 + cb + lane, nf, p.T);
+                    const FramePos po = frame_pos(f0 + cb + lane, nf, p.T, p.t_magic, p.cpc);
                     if (cb + lane < 2 * HW && po.ok) {
                         float* oc = p.out + (long long)(clip0 + po.c) * F * p.T + po.t;
                         const float* src = ft + cb + lane;
@@ -401,23 +441,24 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
             //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
             // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
             // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
-            const int TC = p.T + 1;
-            float* ctile;
+            const int TC = p.T + 1 + (p.T & 1);              // odd row stride of the coefficient tile
+            const int warp = tid >> 5, nwarps = nthr >> 5;
+            float* ctile = reinterpret_cast<float*>(smem + p.sm_ctile);
             if (p.use_mma) {
-                // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels
-                float* dtab = reinterpret_cast<float*>(scratch_all);          // [nt8*8][DS], aliases the FFT scratch
-                const int DS = p.n_filt + 4;
-                ctile = dtab + p.nt8 * 8 * DS;
-                const int q4n = p.n_filt >> 2;
-                for (int idx = tid; idx < p.nt8 * 8 * q4n; idx += nthr) {
-                    const int row = idx / q4n, c4 = idx - row * q4n;
-                    *reinterpret_cast<float4*>(dtab + row * DS + 4 * c4) =
-                        __ldg(reinterpret_cast<const float4*>(p.dct_kf + row * p.n_filt) + c4);
-                }
+                // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels.
+                // D lives in shared memory pre-split into TF32 (hi, lo) pairs: resident for the CTA's lifetime
+                // when it fits, otherwise rebuilt per clip on top of the idle FFT scratch.
+                const float4* dtab = reinterpret_cast<const float4*>(smem + p.sm_dtab);
+                const int RS4 = (p.n_filt >> 3) * 4 + 4;
+                if (!p.dtab_resident) load_dtab(p, reinterpret_cast<float4*>(smem + p.sm_dtab), warp, nwarps, lane);
+                if (p.dct_ksplit > 1)
+                    for (int idx = tid; idx < p.n_mfcc * TC; idx += nthr) ctile[idx] = 0.f;
                 __syncthreads();
-                const int warp = tid >> 5, g = lane >> 2, qq = lane & 3;
+                const int g = lane >> 2, qq = lane & 3;
                 const int mtiles = (p.T + 15) >> 4;
-                for (int mt = warp; mt < mtiles; mt += (nthr >> 5)) {
+                const int kper = (p.n_filt >> 3) / p.dct_ksplit;
+                for (int task = warp; task < mtiles * p.dct_ksplit; task += nwarps) {
+                    const int mt = task / p.dct_ksplit, kpart = task - mt * p.dct_ksplit;
                     float acc[8][4];
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -426,63 +467,77 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                     const float* ra = tile + tra * p.tile_stride + qq;
                     const float* rb = tile + trb * p.tile_stride + qq;
                     const float ca = fmaxf(fmean[tra], thr), cb = fmaxf(fmean[trb], thr);
-                    for (int ks = 0; ks < (p.n_filt >> 3); ++ks) {
+                    for (int ks = kpart * kper; ks < (kpart + 1) * kper; ++ks) {
                         uint32_t ah[4], al[4];
                         split_tf32(fmaxf(ra[8 * ks], thr) - ca, ah[0], al[0]);
                         split_tf32(fmaxf(rb[8 * ks], thr) - cb, ah[1], al[1]);
                         split_tf32(fmaxf(ra[8 * ks + 4], thr) - ca, ah[2], al[2]);
                         split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
+                        // the three 3xTF32 products are issued product-major so that consecutive HMMAs hit
+                        // different accumulators (no back-to-back dependency on one tile)
+                        float4 bf[8];
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) {
-                            if (nt < p.nt8) {
-                                const float* dr = dtab + (nt * 8 + g) * DS + 8 * ks + qq;
-                                uint32_t bh0, bl0, bh1, bl1;
-                                split_tf32(dr[0], bh0, bl0);
-                                split_tf32(dr[4], bh1, bl1);
-                                mma_tf32(acc[nt], al, bh0, bh1);
-                                mma_tf32(acc[nt], ah, bl0, bl1);
-                                mma_tf32(acc[nt], ah, bh0, bh1);
-                            }
-                        }
+                        for (int nt = 0; nt < 8; ++nt)
+                            if (nt < p.nt8) bf[nt] = dtab[(nt * 8 + g) * RS4 + 4 * ks + qq];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            if (nt < p.nt8) mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            if (nt < p.nt8) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            if (nt < p.nt8) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
                     }
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         if (nt < p.nt8) {
                             const int k = nt * 8 + 2 * qq, ta = t0 + g, tb = t0 + g + 8;
-                            if (k == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
-                            if (k < p.n_mfcc) {
-                                if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
-                                if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
-                            }
-                            if (k + 1 < p.n_mfcc) {
-                                if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
-                                if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
+                            if (k == 0 && kpart == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
+                            if (p.dct_ksplit > 1) {
+                                if (k < p.n_mfcc) {
+                                    if (ta < p.T) atomicAdd(ctile + k * TC + ta, acc[nt][0]);
+                                    if (tb < p.T) atomicAdd(ctile + k * TC + tb, acc[nt][2]);
+                                }
+                                if (k + 1 < p.n_mfcc) {
+                                    if (ta < p.T) atomicAdd(ctile + (k + 1) * TC + ta, acc[nt][1]);
+                                    if (tb < p.T) atomicAdd(ctile + (k + 1) * TC + tb, acc[nt][3]);
+                                }
+                            } else {
+                                if (k < p.n_mfcc) {
+                                    if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
+                                    if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
+                                }
+                                if (k + 1 < p.n_mfcc) {
+                                    if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
+                                    if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
+                                }
                             }
                         }
                     }
                 }
             } else {
-                ctile = reinterpret_cast<float*>(scratch_all);
                 const int kq_n = p.n_mfcc_pad / 4;
-                for (int task = tid; task < p.T * kq_n; task += nthr) {
-                    const int t = task % p.T, kq = task / p.T;
-                    const float* row = tile + t * p.tile_stride;
+                for (int kq = warp; kq < kq_n; kq += nwarps) {
                     const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float ct = fmaxf(fmean[t], thr);
+                    for (int t = lane; t < p.T; t += 32) {
+                        const float* row = tile + t * p.tile_stride;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float ct = fmaxf(fmean[t], thr);
 #pragma unroll 4
-                    for (int f = 0; f < p.n_filt; ++f) {
-                        const float d = fmaxf(row[f], thr) - ct;
-                        const float4 w = __ldg(dcol + f * kq_n);
-                        acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
-                        acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+                        for (int f = 0; f < p.n_filt; ++f) {
+                            const float d = fmaxf(row[f], thr) - ct;
+                            const float4 w = __ldg(dcol + f * kq_n);
+                            acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
+                            acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
+                        }
+                        const int k0 = 4 * kq;
+                        if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
+                        ctile[(k0 + 0) * TC + t] = acc.x;
+                        if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
+                        if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
+                        if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
                     }
-                    const int k0 = 4 * kq;
-                    if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
-                    ctile[(k0 + 0) * TC + t] = acc.x;
-                    if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
-                    if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
-                    if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
                 }
             }
             __syncthreads();
@@ -490,23 +545,26 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
             for (int d = 1; d <= p.n_deltas; ++d) {
                 const float* src = ctile + (d - 1) * p.n_mfcc * TC;
                 float* dst = ctile + d * p.n_mfcc * TC;
-                for (int idx = tid; idx < p.n_mfcc * p.T; idx += nthr) {
-                    const int k = idx / p.T, t = idx % p.T;
-                    const float* s = src + k * TC;
-                    float g;
-                    if (t == 0) g = s[1] - s[0];
-                    else if (t == p.T - 1) g = s[t] - s[t - 1];
-                    else g = 0.5f * (s[t + 1] - s[t - 1]);
-                    dst[k * TC + t] = g;
+                for (int k = warp; k < p.n_mfcc; k += nwarps) {
+                    const float* sr = src + k * TC;
+                    for (int t = lane; t < p.T; t += 32) {
+                        float gr;
+                        if (t == 0) gr = sr[1] - sr[0];
+                        else if (t == p.T - 1) gr = sr[t] - sr[t - 1];
+                        else gr = 0.5f * (sr[t + 1] - sr[t - 1]);
+                        dst[k * TC + t] = gr;
+                    }
                 }
                 __syncthreads();
             }
             const int R = (1 + p.n_deltas) * p.n_mfcc;
             float* oc = p.out + (long long)clip0 * R * p.T;
             if (p.layout == SRFE_LAYOUT_FT) {
-                for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx / p.T) * TC + idx % p.T];
+                for (int r = warp; r < R; r += nwarps)
+                    for (int t = lane; t < p.T; t += 32) oc[r * p.T + t] = ctile[r * TC + t];
             } else {
-                for (int idx = tid; idx < R * p.T; idx += nthr) oc[idx] = ctile[(idx % R) * TC + idx / R];
+                for (int t = warp; t < p.T; t += nwarps)
+                    for (int r = lane; r < R; r += 32) oc[t * R + r] = ctile[r * TC + t];
             }
             __syncthreads();                                // scratch / tile are reused by the next clip
         }
