@@ -40,6 +40,8 @@ struct Entry {
     void* d_blob = nullptr;
     void* d_dct = nullptr;
     void* d_dct_kf = nullptr;
+    int mel_ng = 0;             // ELL shape: groups and 2-bit run-length code (0 groups = not encodable)
+    unsigned mel_code = 0;
     int n_bins = 0;
 };
 
@@ -108,9 +110,16 @@ static void add_fft_tables(BlobBuilder& bb, KParams& kp, int n_fft, const std::v
     window_range(win, kp.w_lo, kp.w_hi);
 }
 
-static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_fft) {
+static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_fft, Entry* e) {
     EllBank ell;
     to_ell(sb, ell);
+    e->mel_ng = ell.groups <= 16 ? ell.groups : 0;
+    e->mel_code = 0;
+    for (int g = 0; g < ell.groups && e->mel_ng; ++g) {
+        const int n4 = ell.gmeta[2 * g + 1];
+        if (n4 < 1 || n4 > 4) { e->mel_ng = 0; break; }
+        e->mel_code |= (unsigned)(n4 - 1) << (2 * g);
+    }
     // the packed power buffer aliases the FFT scratch: the padded runs must stay inside it
     const int cap = (n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 2;    // P2 slots
     if (ell.max_reach > cap) return fail(SRFE_ERR_UNSUPPORTED, "filterbank too wide for the shared-memory power buffer");
@@ -119,8 +128,6 @@ static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_ff
     kp.off_fw4 = bb.add(ell.w4.data(), ell.w4.size() * 4);
     kp.n_filt = (int)sb.start.size();
     kp.n_fgroups = ell.groups;
-    kp.ell_n4max = 0;
-    for (int g = 0; g < ell.groups; ++g) kp.ell_n4max = std::max(kp.ell_n4max, ell.gmeta[2 * g + 1]);
     return SRFE_OK;
 }
 
@@ -173,7 +180,7 @@ static int build_entry(const srfe_fbank_params& p, Entry* e) {
     to_sparse(dense, p.nfilt, p.n_fft / 2 + 1, 0.25 / (double)p.n_fft, sb);   // |X|^2 / NFFT (model_fbanks_cnn.py:43)
     BlobBuilder bb;
     add_fft_tables(bb, e->kp, p.n_fft, win);
-    { int rc = add_bank(bb, e->kp, sb, p.n_fft); if (rc != SRFE_OK) return rc; }
+    { int rc = add_bank(bb, e->kp, sb, p.n_fft, e); if (rc != SRFE_OK) return rc; }
     e->n_fft = p.n_fft;
     e->n_bins = p.n_fft / 2 + 1;
     e->kp.hop = p.frame_step;
@@ -192,7 +199,7 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     to_sparse(dense, p.n_mels, p.n_fft / 2 + 1, 0.25, sb);
     BlobBuilder bb;
     add_fft_tables(bb, e->kp, p.n_fft, win);
-    { int rc = add_bank(bb, e->kp, sb, p.n_fft); if (rc != SRFE_OK) return rc; }
+    { int rc = add_bank(bb, e->kp, sb, p.n_fft, e); if (rc != SRFE_OK) return rc; }
     e->n_fft = p.n_fft;
     e->n_bins = p.n_fft / 2 + 1;
     e->kp.hop = p.hop;
@@ -239,9 +246,9 @@ static int dev_info(DevInfo** out) {
     return SRFE_OK;
 }
 
-template <int NFFT, int FAM, int JLO, int JHI, int MAXT, bool PF>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE>
 static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, MAXT, PF>;
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
@@ -259,10 +266,15 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
     return SRFE_OK;
 }
 
+// mel-bank shapes with a fully unrolled projection: {8 groups, code 0xa400} = 128 Slaney mels @ n_fft 512 and the
+// reference's 120 HTK bands @ 512; {8, 0xe500} = 128 Slaney mels @ n_fft 640.  Anything else: runtime metadata.
 template <int NFFT, int FAM, int JLO, int JHI>
-static int launch_t(const KParams& kp, int grid, int threads, int smem_bytes, bool prefetch, cudaStream_t st) {
-    if (prefetch && threads <= 384) return launch_k<NFFT, FAM, JLO, JHI, 384, true>(kp, grid, threads, smem_bytes, st);
-    return launch_k<NFFT, FAM, JLO, JHI, 512, false>(kp, grid, threads, smem_bytes, st);
+static int launch_t(const Entry* e, const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
+    if (FAM != FAM_SPEC) {
+        if (e->mel_ng == 8 && e->mel_code == 0xa400u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u>(kp, grid, threads, smem_bytes, st);
+        if (e->mel_ng == 8 && e->mel_code == 0xe500u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xe500u>(kp, grid, threads, smem_bytes, st);
+    }
+    return launch_k<NFFT, FAM, JLO, JHI, 0, 0u>(kp, grid, threads, smem_bytes, st);
 }
 
 struct Config { int warps, ctas, cpc, smem, scratch, tile, dtab_off, ctile_off, dtab_resident; };
@@ -387,9 +399,7 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
     // window extent in units of 32 samples; known extents get a specialised instantiation
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
-    // register-prefetch flavour (168 regs): only when all resident warps fit the register file
-    const bool prefetch = env_int("SRFE_PREFETCH", 0) != 0 && cfg.ctas * cfg.warps <= 12;
-#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(kp, grid, threads, smem, prefetch, st)
+#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(e, kp, grid, threads, smem, st)
     if (e->n_fft == 512) {
         switch (e->family) {
             case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16);

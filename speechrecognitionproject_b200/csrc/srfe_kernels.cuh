@@ -44,7 +44,6 @@ struct KParams {
     int T, hop, start0;
     int cpc, n_groups;                 // clips per group, number of groups
     unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
-    int ell_n4max;                     // max float4 steps of any 16-filter group (<= 4: unrolled path)
     int sm_ctile, dct_ksplit;          // coefficient tile offset; K split of the DCT over warps (1, 2 or 4)
     int sm_dtab, dtab_resident;        // tensor-core DCT: pre-split (hi, lo) table, loaded once per CTA when it fits
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
@@ -157,6 +156,9 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// lg2.approx with flush-to-zero: no denormal guard code (arguments are bounded below by eps / amin)
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 struct KParams;
 // DCT-II rows -> shared memory, pre-split into TF32 (hi, lo) pairs for the 3xTF32 products
 // layout: float4 {hi(f), hi(f+4), lo(f), lo(f+4)} per (row, k-step, q), f = 8 ks + q: exactly the B fragments of
@@ -190,10 +192,11 @@ __device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int wa
 // --------------------------------------------------------------------------------
 // the fused kernel
 // --------------------------------------------------------------------------------
-// MAXT / PF: two register budgets -- (512 threads, 128 regs, fetch at the top of the round) and
-// (384 threads, 168 regs, next pair prefetched into registers during the output stage)
-template <int NFFT, int FAM, int JLO, int JHI, int MAXT, bool PF>
-__global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
+// NG / CODE: compile-time shape of the mel ELL bank (NG 16-filter groups, 2 bits per group = float4 steps - 1)
+// for the known presets, so the projection unrolls into straight-line code; NG = 0 -> runtime metadata.
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE>
+__global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
+    constexpr bool PF = false;                              // register prefetch of the next pair: measured, no gain
     typedef FftGeom<NFFT> G;
     constexpr int NJ = JHI - JLO;
     constexpr int F = G::M + 1;
@@ -292,17 +295,21 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                         for (int r = 0; r < G::M / 32; ++r) {
                             const int k = l + 16 * r;
                             const float sc = (r == 0 && l == 0) ? p.scale : s2;
-                            float a0 = pa[r].lo * sc, a1 = pa[r].hi * sc, b0 = pb[r].lo * sc, b1 = pb[r].hi * sc;
-                            if (p.take_log) {
-                                a0 = __logf(a0 + p.log_eps); a1 = __logf(a1 + p.log_eps);
-                                b0 = __logf(b0 + p.log_eps); b1 = __logf(b1 + p.log_eps);
+                            float a0, a1, b0, b1;
+                            if (p.take_log) {               // ln(S + eps) = ln2 * lg2(fma(P, scale, eps))
+                                a0 = 0.6931471805599453f * lg2_ftz(fmaf(pa[r].lo, sc, p.log_eps));
+                                a1 = 0.6931471805599453f * lg2_ftz(fmaf(pa[r].hi, sc, p.log_eps));
+                                b0 = 0.6931471805599453f * lg2_ftz(fmaf(pb[r].lo, sc, p.log_eps));
+                                b1 = 0.6931471805599453f * lg2_ftz(fmaf(pb[r].hi, sc, p.log_eps));
+                            } else {
+                                a0 = pa[r].lo * sc; a1 = pa[r].hi * sc; b0 = pb[r].lo * sc; b1 = pb[r].hi * sc;
                             }
                             if (cA.ok) { rowA[k] = a0; rowA[G::M - k] = b0; }
                             if (cB.ok) { rowB[k] = a1; rowB[G::M - k] = b1; }
                         }
                         if (l == 0) {
                             float c0 = pmid.lo * s2, c1 = pmid.hi * s2;
-                            if (p.take_log) { c0 = __logf(c0 + p.log_eps); c1 = __logf(c1 + p.log_eps); }
+                            if (p.take_log) { c0 = 0.6931471805599453f * lg2_ftz(c0 + p.log_eps); c1 = 0.6931471805599453f * lg2_ftz(c1 + p.log_eps); }
                             if (cA.ok) rowA[G::M / 2] = c0;
                             if (cB.ok) rowB[G::M / 2] = c1;
                         }
@@ -313,15 +320,18 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
 #pragma unroll
                         for (int r = 0; r < G::M / 32; ++r) {
                             const float sc = (r == 0 && l == 0) ? p.scale : s2b;
-                            pa[r] = pmul(pa[r], bc(sc));
-                            pb[r] = pmul(pb[r], bc(sc));
                             if (p.take_log) {
-                                pa[r] = mkp(__logf(pa[r].lo + p.log_eps), __logf(pa[r].hi + p.log_eps));
-                                pb[r] = mkp(__logf(pb[r].lo + p.log_eps), __logf(pb[r].hi + p.log_eps));
+                                pa[r] = pfma(pa[r], bc(sc), bc(p.log_eps));
+                                pb[r] = pfma(pb[r], bc(sc), bc(p.log_eps));
+                                pa[r] = mkp(0.6931471805599453f * lg2_ftz(pa[r].lo), 0.6931471805599453f * lg2_ftz(pa[r].hi));
+                                pb[r] = mkp(0.6931471805599453f * lg2_ftz(pb[r].lo), 0.6931471805599453f * lg2_ftz(pb[r].hi));
+                            } else {
+                                pa[r] = pmul(pa[r], bc(sc));
+                                pb[r] = pmul(pb[r], bc(sc));
                             }
                         }
                         pmid = pmul(pmid, bc(s2b));
-                        if (p.take_log) pmid = mkp(__logf(pmid.lo + p.log_eps), __logf(pmid.hi + p.log_eps));
+                        if (p.take_log) pmid = mkp(0.6931471805599453f * lg2_ftz(pmid.lo + p.log_eps), 0.6931471805599453f * lg2_ftz(pmid.hi + p.log_eps));
                     }
                 } else {
                     // power -> shared as (A, B) pairs (aliases the FFT scratch), then sparse triangular sums:
@@ -341,16 +351,36 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                     float* orowB = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * p.n_filt
                                                       : tile + (cB.ok ? cB.t : p.T) * p.tile_stride;
                     P2 fsum = bc(0.f);
-                    for (int i = 0; i < p.n_fgroups; ++i) {
-                        const int2 gm = g_meta[i];
-                        const int m = 16 * i + l;
-                        const P2* pq = pbuf + f_start[m];
-                        const float4* wq = f_w4 + gm.x * 16 + l;
-                        P2 acc = bc(0.f);
-                        if (p.ell_n4max <= 4) {
+                    // one filter per lane and group; emit() turns the band sum into dB and stores it
+                    auto emit = [&](int m, const P2& acc, bool guard) {
+                        if (guard && m >= p.n_filt) return;
+                        if (FAM == FAM_FBANK) {
+                            float a = acc.lo, b = acc.hi;
+                            if (a == 0.f) a = 2.220446049250313e-16f;                  // model_fbanks_cnn.py:61
+                            if (b == 0.f) b = 2.220446049250313e-16f;
+                            if (cA.ok) orowA[m] = 6.020599913279624f * __log2f(a);      // 20 log10
+                            if (cB.ok) orowB[m] = 6.020599913279624f * __log2f(b);
+                        } else {
+                            const float da = 3.010299956639812f * lg2_ftz(fmaxf(acc.lo, p.amin));   // 10 log10
+                            const float db = 3.010299956639812f * lg2_ftz(fmaxf(acc.hi, p.amin));
+                            orowA[m] = da;                      // invalid frames go to the dummy row T
+                            orowB[m] = db;
+                            run_max = fmaxf(run_max, fmaxf(cA.ok ? da : -CUDART_INF_F, cB.ok ? db : -CUDART_INF_F));
+                            fsum = padd(fsum, mkp(da, db));
+                        }
+                    };
+                    if (NG > 0) {
+                        int off4 = 0;                       // all of this folds at compile time
+#pragma unroll
+                        for (int i = 0; i < NG; ++i) {
+                            const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
+                            const int m = 16 * i + l;
+                            const P2* pq = pbuf + f_start[m];
+                            const float4* wq = f_w4 + off4 * 16 + l;
+                            P2 acc = bc(0.f);
 #pragma unroll
                             for (int q4 = 0; q4 < 4; ++q4) {
-                                if (q4 < gm.y) {            // uniform over the warp
+                                if (q4 < n4) {
                                     const float4 w = wq[q4 * 16];
                                     acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
                                     acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
@@ -358,7 +388,16 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                                     acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
                                 }
                             }
-                        } else {
+                            off4 += n4;
+                            emit(m, acc, i == NG - 1);
+                        }
+                    } else {
+                        for (int i = 0; i < p.n_fgroups; ++i) {
+                            const int2 gm = g_meta[i];
+                            const int m = 16 * i + l;
+                            const P2* pq = pbuf + f_start[m];
+                            const float4* wq = f_w4 + gm.x * 16 + l;
+                            P2 acc = bc(0.f);
                             for (int q4 = 0; q4 < gm.y; ++q4) {
                                 const float4 w = wq[q4 * 16];
                                 acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
@@ -366,22 +405,7 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
                                 acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
                                 acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
                             }
-                        }
-                        if (m < p.n_filt) {
-                            if (FAM == FAM_FBANK) {
-                                float a = acc.lo, b = acc.hi;
-                                if (a == 0.f) a = 2.220446049250313e-16f;              // model_fbanks_cnn.py:61
-                                if (b == 0.f) b = 2.220446049250313e-16f;
-                                if (cA.ok) orowA[m] = 6.020599913279624f * __log2f(a);  // 20 log10
-                                if (cB.ok) orowB[m] = 6.020599913279624f * __log2f(b);
-                            } else {
-                                const float da = 3.010299956639812f * __log2f(fmaxf(acc.lo, p.amin));   // 10 log10
-                                const float db = 3.010299956639812f * __log2f(fmaxf(acc.hi, p.amin));
-                                orowA[m] = da;                  // invalid frames go to the dummy row T
-                                orowB[m] = db;
-                                run_max = fmaxf(run_max, fmaxf(cA.ok ? da : -CUDART_INF_F, cB.ok ? db : -CUDART_INF_F));
-                                fsum = padd(fsum, mkp(da, db));
-                            }
+                            emit(m, acc, true);
                         }
                     }
                     if (FAM == FAM_MFCC) {                   // per-frame mean dB: centre of the DCT accumulation
@@ -429,7 +453,7 @@ __global__ void __launch_bounds__(MAXT, 1) srfe_kernel(const KParams p) {
         }
 
         if (FAM == FAM_MFCC) {
-            __shared__ float s_red[MAXT / 32];
+            __shared__ float s_red[kMaxThreads / 32];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
             if ((tid & 31) == 0) s_red[tid >> 5] = run_max;
