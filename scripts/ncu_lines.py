@@ -5,8 +5,8 @@ src_csv, so = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 rows = list(csv.reader(open(src_csv)))
 kname = rows[0][1]
-m = re.search(r"srfe_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d)>", kname)
-mangled = "srfe_kernelILi%sELi%sELi%sELi%sELi%sELb%sEE" % m.groups()
+m = re.search(r"srfe_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(unsigned int\)(\d+)>", kname)
+mangled = "srfe_kernelILi%sELi%sELi%sELi%sELi%sELj%sEE" % m.groups()
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]; body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
 ci = {h: i for i, h in enumerate(hdr)}

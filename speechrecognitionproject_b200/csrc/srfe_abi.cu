@@ -246,9 +246,9 @@ static int dev_info(DevInfo** out) {
     return SRFE_OK;
 }
 
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8>
 static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE>;
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, NT8>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
@@ -270,11 +270,16 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
 // reference's 120 HTK bands @ 512; {8, 0xe500} = 128 Slaney mels @ n_fft 640.  Anything else: runtime metadata.
 template <int NFFT, int FAM, int JLO, int JHI>
 static int launch_t(const Entry* e, const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    if (FAM != FAM_SPEC) {
-        if (e->mel_ng == 8 && e->mel_code == 0xa400u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u>(kp, grid, threads, smem_bytes, st);
-        if (e->mel_ng == 8 && e->mel_code == 0xe500u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xe500u>(kp, grid, threads, smem_bytes, st);
+    if (FAM == FAM_FBANK) {
+        if (e->mel_ng == 8 && e->mel_code == 0xa400u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u, 0>(kp, grid, threads, smem_bytes, st);
     }
-    return launch_k<NFFT, FAM, JLO, JHI, 0, 0u>(kp, grid, threads, smem_bytes, st);
+    if (FAM == FAM_MFCC && kp.use_mma) {      // preset-shaped instantiations: (mel bank shape, DCT N-tiles)
+        if (NFFT == 512 && e->mel_ng == 8 && e->mel_code == 0xa400u && kp.nt8 == 5)
+            return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u, 5>(kp, grid, threads, smem_bytes, st);
+        if (NFFT == 640 && e->mel_ng == 8 && e->mel_code == 0xe500u && kp.nt8 == 2)
+            return launch_k<NFFT, FAM, JLO, JHI, 8, 0xe500u, 2>(kp, grid, threads, smem_bytes, st);
+    }
+    return launch_k<NFFT, FAM, JLO, JHI, 0, 0u, 0>(kp, grid, threads, smem_bytes, st);
 }
 
 struct Config { int warps, ctas, cpc, smem, scratch, tile, dtab_off, ctile_off, dtab_resident; };

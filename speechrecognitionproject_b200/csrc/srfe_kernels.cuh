@@ -194,7 +194,9 @@ __device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int wa
 // --------------------------------------------------------------------------------
 // NG / CODE: compile-time shape of the mel ELL bank (NG 16-filter groups, 2 bits per group = float4 steps - 1)
 // for the known presets, so the projection unrolls into straight-line code; NG = 0 -> runtime metadata.
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE>
+// NT8: compile-time number of 8-coefficient N-tiles of the tensor-core DCT (0 = runtime p.nt8): a constant
+// trip count keeps the mma.sync sequence free of predicates / WARPSYNCs.
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8>
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     constexpr bool PF = false;                              // register prefetch of the next pair: measured, no gain
     typedef FftGeom<NFFT> G;
@@ -481,11 +483,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 const int g = lane >> 2, qq = lane & 3;
                 const int mtiles = (p.T + 15) >> 4;
                 const int kper = (p.n_filt >> 3) / p.dct_ksplit;
+                constexpr int NTC = NT8 > 0 ? NT8 : 8;      // unrolled N-tile count
+                const int ntn = NT8 > 0 ? NT8 : p.nt8;      // live N-tiles (== NTC when specialised)
+                const float4* dbase = dtab + g * RS4 + qq;
                 for (int task = warp; task < mtiles * p.dct_ksplit; task += nwarps) {
                     const int mt = task / p.dct_ksplit, kpart = task - mt * p.dct_ksplit;
-                    float acc[8][4];
+                    float acc[NTC][4];
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+                    for (int nt = 0; nt < NTC; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
                     const int t0 = mt * 16;
                     const int tra = min(t0 + g, p.T - 1), trb = min(t0 + g + 8, p.T - 1);
                     const float* ra = tile + tra * p.tile_stride + qq;
@@ -499,42 +504,52 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                         split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
                         // the three 3xTF32 products are issued product-major so that consecutive HMMAs hit
                         // different accumulators (no back-to-back dependency on one tile)
-                        float4 bf[8];
+                        const float4* dk = dbase + 4 * ks;
+                        float4 bf[NTC];
+                        if (NT8 > 0) {
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            if (nt < p.nt8) bf[nt] = dtab[(nt * 8 + g) * RS4 + 4 * ks + qq];
+                            for (int nt = 0; nt < NTC; ++nt) bf[nt] = dk[nt * 8 * RS4];
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            if (nt < p.nt8) mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            if (nt < p.nt8) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
+                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            if (nt < p.nt8) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+                        } else {
+#pragma unroll
+                            for (int nt = 0; nt < NTC; ++nt) {
+                                if (nt < ntn) {             // warp-uniform
+                                    bf[nt] = dk[nt * 8 * RS4];
+                                    mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+                                    mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
+                                    mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+                                }
+                            }
+                        }
                     }
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt) {
-                        if (nt < p.nt8) {
+                    for (int nt = 0; nt < NTC; ++nt) {
+                        if (nt < ntn) {
                             const int k = nt * 8 + 2 * qq, ta = t0 + g, tb = t0 + g + 8;
                             if (k == 0 && kpart == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
+                            float* c0p = ctile + k * TC;
                             if (p.dct_ksplit > 1) {
                                 if (k < p.n_mfcc) {
-                                    if (ta < p.T) atomicAdd(ctile + k * TC + ta, acc[nt][0]);
-                                    if (tb < p.T) atomicAdd(ctile + k * TC + tb, acc[nt][2]);
+                                    if (ta < p.T) atomicAdd(c0p + ta, acc[nt][0]);
+                                    if (tb < p.T) atomicAdd(c0p + tb, acc[nt][2]);
                                 }
                                 if (k + 1 < p.n_mfcc) {
-                                    if (ta < p.T) atomicAdd(ctile + (k + 1) * TC + ta, acc[nt][1]);
-                                    if (tb < p.T) atomicAdd(ctile + (k + 1) * TC + tb, acc[nt][3]);
+                                    if (ta < p.T) atomicAdd(c0p + TC + ta, acc[nt][1]);
+                                    if (tb < p.T) atomicAdd(c0p + TC + tb, acc[nt][3]);
                                 }
                             } else {
                                 if (k < p.n_mfcc) {
-                                    if (ta < p.T) ctile[k * TC + ta] = acc[nt][0];
-                                    if (tb < p.T) ctile[k * TC + tb] = acc[nt][2];
+                                    if (ta < p.T) c0p[ta] = acc[nt][0];
+                                    if (tb < p.T) c0p[tb] = acc[nt][2];
                                 }
                                 if (k + 1 < p.n_mfcc) {
-                                    if (ta < p.T) ctile[(k + 1) * TC + ta] = acc[nt][1];
-                                    if (tb < p.T) ctile[(k + 1) * TC + tb] = acc[nt][3];
+                                    if (ta < p.T) c0p[TC + ta] = acc[nt][1];
+                                    if (tb < p.T) c0p[TC + tb] = acc[nt][3];
                                 }
                             }
                         }
@@ -584,11 +599,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const int R = (1 + p.n_deltas) * p.n_mfcc;
             float* oc = p.out + (long long)clip0 * R * p.T;
             if (p.layout == SRFE_LAYOUT_FT) {
-                for (int r = warp; r < R; r += nwarps)
-                    for (int t = lane; t < p.T; t += 32) oc[r * p.T + t] = ctile[r * TC + t];
+                for (int r = warp; r < R; r += nwarps) {
+                    float* orow = oc + r * p.T;
+                    const float* crow = ctile + r * TC;
+                    for (int t = lane; t < p.T; t += 32) orow[t] = crow[t];
+                }
             } else {
-                for (int t = warp; t < p.T; t += nwarps)
-                    for (int r = lane; r < R; r += 32) oc[t * R + r] = ctile[r * TC + t];
+                for (int t = warp; t < p.T; t += nwarps) {
+                    float* orow = oc + t * R;
+                    const float* ccol = ctile + t;
+                    for (int r = lane; r < R; r += 32) orow[r] = ccol[r * TC];
+                }
             }
             __syncthreads();                                // scratch / tile are reused by the next clip
         }
