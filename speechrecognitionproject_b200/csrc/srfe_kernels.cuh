@@ -172,7 +172,7 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
     FramePos r;
     r.ok = f < nf;
     const int fc = r.ok ? f : (nf - 1);                     // invalid frames alias the last valid one (outputs suppressed)
-    r.c = (cpc == 1) ? 0 : (int)__umulhi((unsigned)fc, magic);
+    r.c = (cpc == 1) ? 0 : (T == 1 ? fc : (int)__umulhi((unsigned)fc, magic));   // T == 1: the magic would be 2^32
     r.t = fc - r.c * T;
     return r;
 }

@@ -238,3 +238,91 @@ def test_launch_counter(srfe_lib, corpus):
     n0 = S.launch_count()
     S.mfcc(x); S.spec(x); S.fbank(x)
     assert S.launch_count() == n0 + 3
+
+
+# ---------------------------------------------------------------- generic (non-preset) shapes ----
+# The presets hit shape-specialised instantiations (compile-time mel bank shape / DCT N-tiles);
+# these cases force the generic code paths: runtime ELL metadata, runtime N-tile count, CUDA-core
+# DCT (n_mels not a multiple of 8), other window / hop / filter counts, short clips.
+GENERIC_MFCC = [
+    S.MfccParams(n_fft=512, win_length=400, hop=160, n_mels=40, n_mfcc=13, n_deltas=2),
+    S.MfccParams(n_fft=512, win_length=512, hop=256, n_mels=64, n_mfcc=20, n_deltas=1),
+    S.MfccParams(n_fft=640, win_length=480, hop=240, n_mels=80, n_mfcc=24, n_deltas=0, top_db=None),
+    S.MfccParams(n_fft=640, hop=320, n_mels=100, n_mfcc=13, n_deltas=2),          # CUDA-core DCT path
+    S.MfccParams(n_fft=512, win_length=320, hop=160, n_mels=128, n_mfcc=64, n_deltas=0, fmin=20.0, fmax=7600.0),
+    S.MfccParams(n_fft=640, hop=320, n_mels=128, n_mfcc=13, n_deltas=2, top_db=40.0),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(GENERIC_MFCC)))
+def test_mfcc_generic_shapes(srfe_lib, corpus, idx):
+    p = GENERIC_MFCC[idx]
+    x = corpus[:6]
+    got = _gpu(S.mfcc, x, p)
+    truth = H.oracle_batch(oracle.mfcc_truth, x, H.to_oracle_params(p))
+    assert got.shape == truth.shape
+    H.check_mfcc(got, truth, f"generic mfcc {idx}")
+    got_tf = _gpu(S.mfcc, x, p, layout="tf")
+    np.testing.assert_array_equal(got_tf, np.ascontiguousarray(got.transpose(0, 2, 1)))
+
+
+GENERIC_FBANK = [
+    S.FbankParams(nfilt=26), S.FbankParams(nfilt=64, frame_len=512, frame_step=128),
+    S.FbankParams(nfft=640, frame_len=640, frame_step=320, nfilt=80, preemph=0.95),
+    S.FbankParams(nfft=640, frame_len=400, frame_step=160, nfilt=120), S.FbankParams(nfilt=200, preemph=0.0),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(GENERIC_FBANK)))
+def test_fbank_generic_shapes(srfe_lib, corpus, idx):
+    p = GENERIC_FBANK[idx]
+    x = corpus[:6]
+    got = _gpu(S.fbank, x, p)
+    truth = H.oracle_batch(oracle.fbank_truth, x, H.to_oracle_params(p))
+    assert got.shape == truth.shape
+    H.check_logmel(got, truth, f"generic fbank {idx}")
+
+
+@pytest.mark.parametrize("nperseg,noverlap", [(512, 384), (640, 0), (512, 0), (640, 512)])
+def test_spec_generic_shapes(srfe_lib, corpus, nperseg, noverlap):
+    x = corpus[:5]
+    for layout in ("ft", "tf"):
+        p = S.SpecParams(nperseg=nperseg, noverlap=noverlap, layout=layout)
+        got = _gpu(S.spec, x, p)
+        truth = H.oracle_batch(oracle.spec_truth, x, H.to_oracle_params(p))
+        assert got.shape == truth.shape
+        H.check_logspec(got, truth, f"spec {nperseg}/{noverlap} {layout}")
+
+
+def test_too_long_for_fused_mfcc_is_an_error_not_a_fallback(srfe_lib):
+    x = torch.zeros(2, 16000, device="cuda")
+    with pytest.raises(RuntimeError, match="SRFE_ERR_TOO_LARGE"):
+        S.mfcc(x, S.MfccParams(n_fft=512, win_length=320, hop=40, n_mels=128, n_mfcc=64, n_deltas=0))
+
+
+def test_short_and_long_clips(srfe_lib):
+    rng = np.random.default_rng(5)
+    for n in (700, 1024, 4000, 32000):
+        x = np.round(rng.standard_normal((3, n)) * 2000).astype(np.float32)
+        got = _gpu(S.mfcc, x, S.R_MFCC)
+        H.check_mfcc(got, H.oracle_batch(oracle.mfcc_truth, x, oracle.R_MFCC), f"mfcc n={n}")
+        got = _gpu(S.fbank, x, S.R_FBANK)
+        H.check_logmel(got, H.oracle_batch(oracle.fbank_truth, x, oracle.R_FBANK), f"fbank n={n}")
+        got = _gpu(S.spec, x, S.R_SPEC, layout="tf")
+        H.check_logspec(got, H.oracle_batch(oracle.spec_truth, x, replace(oracle.R_SPEC, layout="tf")), f"spec n={n}")
+
+
+def test_large_batch_properties(srfe_lib):
+    """Full-size batch (BASELINE cfg2/cfg3 sizes): size-independent properties instead of a CPU oracle run --
+    every clip equals its stand-alone result, duplicated clips give identical features, silence gives the known constants."""
+    torch.manual_seed(0)
+    B = 4096
+    x = (torch.randn(B, 16000, device="cuda") * 2500).round()
+    x[1000] = x[7]; x[4095] = x[7]; x[2048] = 0
+    for fn, p in ((S.spec, S.C_SPEC), (S.fbank, S.C_FBANK), (S.mfcc, S.C_MFCC), (S.mfcc, S.R_MFCC)):
+        y = fn(x, p)
+        assert torch.isfinite(y).all()
+        assert torch.equal(y[1000], y[7]) and torch.equal(y[4095], y[7])
+        for i in (0, 7, 2048, 4095):
+            assert torch.equal(fn(x[i:i + 1], p)[0], y[i])
+    assert torch.allclose(S.mfcc(x[2048:2049], S.R_MFCC)[0, 0], torch.tensor(-100.0 * 128 ** 0.5, device="cuda"), atol=1e-3)
