@@ -30,7 +30,8 @@
  *   - the caller owns `pcm` and `out`; the library owns only immutable tables.
  *   - pcm: float32, `n_clips` rows of `n_samples`, row stride `clip_stride`
  *     elements (>= n_samples), int16-scale values as dataset.py:117 produces.
- *     Rows must be 8-byte aligned (clip_stride even, base 8-byte aligned).
+ *     Rows must be 8-byte aligned (clip_stride even, base 8-byte aligned).  The *_i16 variants take the same
+ *     layout with int16 samples (rows 4-byte aligned).
  *   - out: contiguous float32, shape given by srfe_*_out_shape().
  */
 #ifndef SRFE_H_
@@ -136,6 +137,17 @@ int srfe_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t
 int srfe_mfcc_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                    const srfe_mfcc_params* p, float* out, void* cuda_stream);
 
+/* int16 ingest: the wav's native sample type (dataset.py:103), converted on load inside the
+ * kernel -- replaces dataset.py:117's astype(float32) for callers that keep PCM as int16 and halves the bytes
+ * that cross PCIe / HBM.  Integer-valued float32 input and its int16 copy give bit-identical features.
+ * Rows must be 4-byte aligned (clip_stride even). */
+int srfe_spec_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_spec_params* p, float* out, void* cuda_stream);
+int srfe_fbank_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_fbank_params* p, float* out, void* cuda_stream);
+int srfe_mfcc_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   const srfe_mfcc_params* p, float* out, void* cuda_stream);
+
 /* ---- host entry points (pcm/out are HOST pointers; synchronous) ----------- */
 /* H2D of the batch, the same kernels, D2H of the features, on `device`.
  * Uses a per-thread pinned staging + device workspace that grows on demand. */
@@ -144,6 +156,13 @@ int srfe_spec_host_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, in
 int srfe_fbank_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                         const srfe_fbank_params* p, float* out, int device);
 int srfe_mfcc_host_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_mfcc_params* p, float* out, int device);
+
+int srfe_spec_host_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_spec_params* p, float* out, int device);
+int srfe_fbank_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_fbank_params* p, float* out, int device);
+int srfe_mfcc_host_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                         const srfe_mfcc_params* p, float* out, int device);
 
 /* ---- introspection for benchmarks / tests --------------------------------- */

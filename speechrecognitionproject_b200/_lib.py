@@ -57,6 +57,12 @@ SYMBOLS = {
     "srfe_spec_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), _vp, _vp]),
     "srfe_fbank_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(FbankParamsC), _vp, _vp]),
     "srfe_mfcc_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(MfccParamsC), _vp, _vp]),
+    "srfe_spec_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), _vp, _vp]),
+    "srfe_fbank_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(FbankParamsC), _vp, _vp]),
+    "srfe_mfcc_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(MfccParamsC), _vp, _vp]),
+    "srfe_spec_host_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), _vp, _i32]),
+    "srfe_fbank_host_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(FbankParamsC), _vp, _i32]),
+    "srfe_mfcc_host_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(MfccParamsC), _vp, _i32]),
     "srfe_spec_host_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), _vp, _i32]),
     "srfe_fbank_host_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(FbankParamsC), _vp, _i32]),
     "srfe_mfcc_host_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(MfccParamsC), _vp, _i32]),

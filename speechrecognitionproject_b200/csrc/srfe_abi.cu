@@ -246,9 +246,9 @@ static int dev_info(DevInfo** out) {
     return SRFE_OK;
 }
 
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8, typename SAMP>
 static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, NT8>;
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, NT8, SAMP>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
@@ -264,22 +264,6 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
     if (e != cudaSuccess) return cuda_fail(e, "srfe_kernel launch");
     g_launches.fetch_add(1);
     return SRFE_OK;
-}
-
-// mel-bank shapes with a fully unrolled projection: {8 groups, code 0xa400} = 128 Slaney mels @ n_fft 512 and the
-// reference's 120 HTK bands @ 512; {8, 0xe500} = 128 Slaney mels @ n_fft 640.  Anything else: runtime metadata.
-template <int NFFT, int FAM, int JLO, int JHI>
-static int launch_t(const Entry* e, const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    if (FAM == FAM_FBANK) {
-        if (e->mel_ng == 8 && e->mel_code == 0xa400u) return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u, 0>(kp, grid, threads, smem_bytes, st);
-    }
-    if (FAM == FAM_MFCC && kp.use_mma) {      // preset-shaped instantiations: (mel bank shape, DCT N-tiles)
-        if (NFFT == 512 && e->mel_ng == 8 && e->mel_code == 0xa400u && kp.nt8 == 5)
-            return launch_k<NFFT, FAM, JLO, JHI, 8, 0xa400u, 5>(kp, grid, threads, smem_bytes, st);
-        if (NFFT == 640 && e->mel_ng == 8 && e->mel_code == 0xe500u && kp.nt8 == 2)
-            return launch_k<NFFT, FAM, JLO, JHI, 8, 0xe500u, 2>(kp, grid, threads, smem_bytes, st);
-    }
-    return launch_k<NFFT, FAM, JLO, JHI, 0, 0u, 0>(kp, grid, threads, smem_bytes, st);
 }
 
 struct Config { int warps, ctas, cpc, smem, scratch, tile, dtab_off, ctile_off, dtab_resident; };
@@ -381,7 +365,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
     return SRFE_OK;
 }
 
-static int launch(const Entry* e, KParams kp, cudaStream_t st) {
+static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     if (e->family == FAM_MFCC && kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
     if (kp.n_clips == 0 || kp.T == 0) return SRFE_OK;
     DevInfo* di = nullptr;
@@ -402,46 +386,59 @@ static int launch(const Entry* e, KParams kp, cudaStream_t st) {
     if (e->family == FAM_MFCC && kp.use_mma) kp.dct_ksplit = dct_ksplit_for(kp, cfg.warps);   // spread the DCT over the warps
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
-    // window extent in units of 32 samples; known extents get a specialised instantiation
+    // Curated instantiation list.  Window extents (units of 32 samples) and the preset shapes of the mel
+    // bank / DCT get specialised kernels; everything else runs the generic ones.
+    //   mel {8 groups, 0xa400}: 128 Slaney mels @ n_fft 512 and the reference's 120 HTK bands @ 512
+    //   mel {8 groups, 0xe500}: 128 Slaney mels @ n_fft 640
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
-#define SRFE_GO(N, FAM, JLO, JHI) return launch_t<N, FAM, JLO, JHI>(e, kp, grid, threads, smem, st)
+    const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
+#define SRFE_GO(N, FAM, JLO, JHI, NG, CODE, NT8)                                                                 \
+    return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, NT8, short>(kp, grid, threads, smem, st)                   \
+               : launch_k<N, FAM, JLO, JHI, NG, CODE, NT8, float>(kp, grid, threads, smem, st)
     if (e->n_fft == 512) {
         switch (e->family) {
-            case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16);
+            case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16, 0, 0u, 0);
             case FAM_FBANK:
-                if (jlo == 0 && jhi <= 13) SRFE_GO(512, FAM_FBANK, 0, 13);
-                SRFE_GO(512, FAM_FBANK, 0, 16);
+                if (jlo == 0 && jhi <= 13) {
+                    if (a400) SRFE_GO(512, FAM_FBANK, 0, 13, 8, 0xa400u, 0);
+                    SRFE_GO(512, FAM_FBANK, 0, 13, 0, 0u, 0);
+                }
+                SRFE_GO(512, FAM_FBANK, 0, 16, 0, 0u, 0);
             default:
-                if (jlo >= 1 && jhi <= 15) SRFE_GO(512, FAM_MFCC, 1, 15);
-                SRFE_GO(512, FAM_MFCC, 0, 16);
+                if (jlo >= 1 && jhi <= 15) {
+                    if (a400 && kp.use_mma && kp.nt8 == 5) SRFE_GO(512, FAM_MFCC, 1, 15, 8, 0xa400u, 5);
+                    SRFE_GO(512, FAM_MFCC, 1, 15, 0, 0u, 0);
+                }
+                SRFE_GO(512, FAM_MFCC, 0, 16, 0, 0u, 0);
         }
     } else {
         switch (e->family) {
-            case FAM_SPEC: SRFE_GO(640, FAM_SPEC, 0, 20);
-            case FAM_FBANK:
-                if (jlo == 0 && jhi <= 13) SRFE_GO(640, FAM_FBANK, 0, 13);
-                SRFE_GO(640, FAM_FBANK, 0, 20);
-            default: SRFE_GO(640, FAM_MFCC, 0, 20);
+            case FAM_SPEC: SRFE_GO(640, FAM_SPEC, 0, 20, 0, 0u, 0);
+            case FAM_FBANK: SRFE_GO(640, FAM_FBANK, 0, 20, 0, 0u, 0);
+            default:
+                if (e500 && kp.use_mma && kp.nt8 == 2) SRFE_GO(640, FAM_MFCC, 0, 20, 8, 0xe500u, 2);
+                SRFE_GO(640, FAM_MFCC, 0, 20, 0, 0u, 0);
         }
     }
 #undef SRFE_GO
 }
 
-static int check_buffers(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const void* p,
+static int check_buffers(const void* pcm, int elem, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const void* p,
                          const float* out) {
     if (!p) return fail(SRFE_ERR_BAD_ARG, "params is NULL");
     if (n_clips < 0 || n_samples <= 0) return fail(SRFE_ERR_BAD_ARG, "n_clips must be >= 0 and n_samples > 0");
     if (n_clips > 0 && (!pcm || !out)) return fail(SRFE_ERR_BAD_ARG, "pcm/out is NULL");
     if (clip_stride < n_samples) return fail(SRFE_ERR_BAD_ARG, "clip_stride < n_samples");
-    if (n_clips > 1 && (clip_stride & 1)) return fail(SRFE_ERR_BAD_ARG, "clip_stride must be even (8-byte aligned rows)");
-    if (((uintptr_t)pcm & 7) || ((uintptr_t)out & 3)) return fail(SRFE_ERR_BAD_ARG, "pcm must be 8-byte aligned, out 4-byte aligned");
+    if (n_clips > 1 && (clip_stride & 1)) return fail(SRFE_ERR_BAD_ARG, "clip_stride must be even (rows aligned to a sample pair)");
+    if (((uintptr_t)pcm & (uintptr_t)(2 * elem - 1)) || ((uintptr_t)out & 3))
+        return fail(SRFE_ERR_BAD_ARG, "pcm must be aligned to a sample pair (8 bytes for float32, 4 for int16), out to 4 bytes");
     if (n_clips > 0x7fffffffLL || n_samples > (1 << 24)) return fail(SRFE_ERR_TOO_LARGE, "n_clips / n_samples too large");
     return SRFE_OK;
 }
 
 template <typename P>
-static int run_device(int family, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const P* p,
-                      float* out, cudaStream_t st, int64_t T) {
+static int run_device(int family, const void* pcm, bool i16, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                      const P* p, float* out, cudaStream_t st, int64_t T) {
     Entry* e = nullptr;
     int rc = get_entry(family, *p, &e);
     if (rc != SRFE_OK) return rc;
@@ -452,7 +449,7 @@ static int run_device(int family, const float* pcm, int64_t n_clips, int64_t n_s
     kp.n_clips = (int)n_clips;
     kp.n_samples = (int)n_samples;
     kp.T = (int)T;
-    return launch(e, kp, st);
+    return launch(e, kp, i16, st);
 }
 
 // ------------------------------------------------------------------------------
@@ -461,7 +458,7 @@ static int run_device(int family, const float* pcm, int64_t n_clips, int64_t n_s
 struct HostWs {
     int device = -1;
     cudaStream_t st[2] = {nullptr, nullptr};
-    float* d_in[2] = {nullptr, nullptr};
+    void* d_in[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
     size_t cap_in = 0, cap_out = 0;
 };
@@ -487,21 +484,23 @@ static int host_ws(int device, size_t in_bytes, size_t out_bytes, HostWs** out) 
 }
 
 template <typename P>
-static int run_host(int family, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const P* p,
-                    float* out, int device, int64_t T, int64_t out_per_clip) {
+static int run_host(int family, const void* pcm, bool i16, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                    const P* p, float* out, int device, int64_t T, int64_t out_per_clip) {
     int prev = 0;
-    if (cudaGetDevice(&prev) != cudaSuccess) return fail(SRFE_ERR_NO_DEVICE, "no CUDA device");
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return fail(SRFE_ERR_NO_DEVICE, "no CUDA device"); }
     SRFE_CUDA(cudaSetDevice(device));
+    const size_t elem = i16 ? 2 : 4;
     const int64_t chunk = n_clips < 2048 ? (n_clips > 0 ? n_clips : 1) : 2048;
     HostWs* w = nullptr;
-    int rc = host_ws(device, (size_t)chunk * n_samples * 4, (size_t)chunk * out_per_clip * 4, &w);
+    int rc = host_ws(device, (size_t)chunk * n_samples * elem, (size_t)chunk * out_per_clip * 4, &w);
     for (int64_t c0 = 0, i = 0; rc == SRFE_OK && c0 < n_clips; c0 += chunk, ++i) {
         const int64_t nc = (n_clips - c0 < chunk) ? n_clips - c0 : chunk;
         const int s = (int)(i & 1);
-        cudaError_t ce = cudaMemcpy2DAsync(w->d_in[s], (size_t)n_samples * 4, pcm + c0 * clip_stride, (size_t)clip_stride * 4,
-                                           (size_t)n_samples * 4, (size_t)nc, cudaMemcpyHostToDevice, w->st[s]);
+        cudaError_t ce = cudaMemcpy2DAsync(w->d_in[s], (size_t)n_samples * elem, (const char*)pcm + (size_t)c0 * clip_stride * elem,
+                                           (size_t)clip_stride * elem, (size_t)n_samples * elem, (size_t)nc,
+                                           cudaMemcpyHostToDevice, w->st[s]);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D"); break; }
-        rc = run_device(family, w->d_in[s], nc, n_samples, n_samples, p, w->d_out[s], w->st[s], T);
+        rc = run_device(family, w->d_in[s], i16, nc, n_samples, n_samples, p, w->d_out[s], w->st[s], T);
         if (rc != SRFE_OK) break;
         ce = cudaMemcpyAsync(out + c0 * out_per_clip, w->d_out[s], (size_t)nc * out_per_clip * 4, cudaMemcpyDeviceToHost, w->st[s]);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "D2H"); break; }
@@ -586,52 +585,99 @@ int srfe_mfcc_dct_f64(const srfe_mfcc_params* p, double* d) { SRFE_VALIDATE(p) s
 
 int srfe_spec_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
                   float* out, void* stream) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
     if (rc != SRFE_OK) return rc;
     const int64_t T = srfe_spec_out_shape(p, n_samples, nullptr);
     if (T < 0) return (int)T;
-    return run_device(FAM_SPEC, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+    return run_device(FAM_SPEC, pcm, false, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
 }
-int srfe_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
-                   float* out, void* stream) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
-    if (rc != SRFE_OK) return rc;
-    const int64_t T = srfe_fbank_out_shape(p, n_samples, nullptr);
-    if (T < 0) return (int)T;
-    return run_device(FAM_FBANK, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
-}
-int srfe_mfcc_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
-                  float* out, void* stream) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
-    if (rc != SRFE_OK) return rc;
-    const int64_t T = srfe_mfcc_out_shape(p, n_samples, nullptr);
-    if (T < 0) return (int)T;
-    return run_device(FAM_MFCC, pcm, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
-}
-
 int srfe_spec_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
                        float* out, int device) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
     if (rc != SRFE_OK) return rc;
     int64_t s[2]; const int64_t T = srfe_spec_out_shape(p, n_samples, s);
     if (T < 0) return (int)T;
-    return run_host(FAM_SPEC, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+    return run_host(FAM_SPEC, pcm, false, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_spec_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_spec_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_SPEC, pcm, true, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+int srfe_spec_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* p,
+                       float* out, int device) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_spec_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_SPEC, pcm, true, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_fbank_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_FBANK, pcm, false, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
 }
 int srfe_fbank_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
-                        float* out, int device) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+                       float* out, int device) {
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
     if (rc != SRFE_OK) return rc;
     int64_t s[2]; const int64_t T = srfe_fbank_out_shape(p, n_samples, s);
     if (T < 0) return (int)T;
-    return run_host(FAM_FBANK, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+    return run_host(FAM_FBANK, pcm, false, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_fbank_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_fbank_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_FBANK, pcm, true, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+int srfe_fbank_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_fbank_params* p,
+                       float* out, int device) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_fbank_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_FBANK, pcm, true, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_mfcc_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_mfcc_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_MFCC, pcm, false, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
 }
 int srfe_mfcc_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
                        float* out, int device) {
-    int rc = check_buffers(pcm, n_clips, n_samples, clip_stride, p, out);
+    int rc = check_buffers(pcm, sizeof(float), n_clips, n_samples, clip_stride, p, out);
     if (rc != SRFE_OK) return rc;
     int64_t s[2]; const int64_t T = srfe_mfcc_out_shape(p, n_samples, s);
     if (T < 0) return (int)T;
-    return run_host(FAM_MFCC, pcm, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+    return run_host(FAM_MFCC, pcm, false, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
+}
+int srfe_mfcc_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
+                  float* out, void* stream) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    const int64_t T = srfe_mfcc_out_shape(p, n_samples, nullptr);
+    if (T < 0) return (int)T;
+    return run_device(FAM_MFCC, pcm, true, n_clips, n_samples, clip_stride, p, out, (cudaStream_t)stream, T);
+}
+int srfe_mfcc_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_mfcc_params* p,
+                       float* out, int device) {
+    int rc = check_buffers(pcm, sizeof(int16_t), n_clips, n_samples, clip_stride, p, out);
+    if (rc != SRFE_OK) return rc;
+    int64_t s[2]; const int64_t T = srfe_mfcc_out_shape(p, n_samples, s);
+    if (T < 0) return (int)T;
+    return run_host(FAM_MFCC, pcm, true, n_clips, n_samples, clip_stride, p, out, device, T, s[0] * s[1]);
 }
 
 }  // extern "C"

@@ -37,7 +37,7 @@ enum Family { FAM_SPEC = 0, FAM_FBANK = 1, FAM_MFCC = 2 };
 constexpr int kMaxThreads = 512;       // <= 16 warps = 32 half-warps (64 frames in flight) per CTA
 
 struct KParams {
-    const float* pcm;
+    const void* pcm;                   // float32 or int16 samples (kernel template parameter SAMP)
     float* out;
     long long clip_stride;
     int n_clips, n_samples;
@@ -67,19 +67,30 @@ struct KParams {
 // --------------------------------------------------------------------------------
 // frame fetch: raw samples for n = 2 l + 32 j (+1), j in [JLO, JHI)
 // --------------------------------------------------------------------------------
-template <int FAM>
-__device__ __forceinline__ float edge_sample(const KParams& p, const float* __restrict__ x, int idx) {
+// sample loads: float32 as the dataset hands it over (dataset.py:117) or the wav's native int16 (dataset.py:103)
+template <typename S> __device__ __forceinline__ float ld1(const S* q);
+template <> __device__ __forceinline__ float ld1<float>(const float* q) { return __ldg(q); }
+template <> __device__ __forceinline__ float ld1<short>(const short* q) { return (float)__ldg(q); }
+template <typename S> __device__ __forceinline__ float2 ld2(const S* q);
+template <> __device__ __forceinline__ float2 ld2<float>(const float* q) { return __ldg(reinterpret_cast<const float2*>(q)); }
+template <> __device__ __forceinline__ float2 ld2<short>(const short* q) {
+    const short2 v = __ldg(reinterpret_cast<const short2*>(q));
+    return make_float2((float)v.x, (float)v.y);
+}
+
+template <int FAM, typename S>
+__device__ __forceinline__ float edge_sample(const KParams& p, const S* __restrict__ x, int idx) {
     if (FAM == FAM_MFCC) {                                  // np.pad(mode='reflect')
         if (idx < 0) idx = -idx;
         if (idx >= p.n_samples) idx = 2 * (p.n_samples - 1) - idx;
-        return __ldg(x + idx);
+        return ld1<S>(x + idx);
     }
     if (FAM == FAM_FBANK) {                                 // zero padding past the clip; e[0] = x[0]
         if (idx >= p.n_samples) return 0.f;
-        const float prev = idx > 0 ? __ldg(x + idx - 1) : 0.f;
-        return __fsub_rn(__ldg(x + idx), __fmul_rn(p.preemph, prev));   // model_fbanks_cnn.py:20 (float32)
+        const float prev = idx > 0 ? ld1<S>(x + idx - 1) : 0.f;
+        return __fsub_rn(ld1<S>(x + idx), __fmul_rn(p.preemph, prev));   // model_fbanks_cnn.py:20 (float32)
     }
-    return (idx >= 0 && idx < p.n_samples) ? __ldg(x + idx) : 0.f;
+    return (idx >= 0 && idx < p.n_samples) ? ld1<S>(x + idx) : 0.f;
 }
 
 template <int FAM, int NJ>
@@ -89,23 +100,23 @@ struct RawFrame {
     bool final_;                       // samples already carry the pre-emphasis (edge path)
 };
 
-template <int FAM, int JLO, int JHI>
-__device__ __forceinline__ void fetch_frame(const KParams& p, const float* __restrict__ x, int base, int l,
+template <int FAM, int JLO, int JHI, typename S>
+__device__ __forceinline__ void fetch_frame(const KParams& p, const S* __restrict__ x, int base, int l,
                                             RawFrame<FAM, JHI - JLO>& r) {
     const bool interior = (base + 32 * JLO >= 0) && (base + 32 * JHI <= p.n_samples);
     r.final_ = !interior;
     if (interior) {
-        const float* xs = x + base + 2 * l;
+        const S* xs = x + base + 2 * l;
 #pragma unroll
         for (int j = JLO; j < JHI; ++j) {
-            r.s[j - JLO] = __ldg(reinterpret_cast<const float2*>(xs + 32 * j));
-            if (FAM == FAM_FBANK) r.prev[j - JLO] = (base + 2 * l + 32 * j > 0) ? __ldg(xs + 32 * j - 1) : 0.f;
+            r.s[j - JLO] = ld2<S>(xs + 32 * j);
+            if (FAM == FAM_FBANK) r.prev[j - JLO] = (base + 2 * l + 32 * j > 0) ? ld1<S>(xs + 32 * j - 1) : 0.f;
         }
     } else {
 #pragma unroll
         for (int j = JLO; j < JHI; ++j) {
             const int i = base + 2 * l + 32 * j;
-            r.s[j - JLO] = make_float2(edge_sample<FAM>(p, x, i), edge_sample<FAM>(p, x, i + 1));
+            r.s[j - JLO] = make_float2(edge_sample<FAM, S>(p, x, i), edge_sample<FAM, S>(p, x, i + 1));
             if (FAM == FAM_FBANK) r.prev[j - JLO] = 0.f;
         }
     }
@@ -196,8 +207,9 @@ __device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int wa
 // for the known presets, so the projection unrolls into straight-line code; NG = 0 -> runtime metadata.
 // NT8: compile-time number of 8-coefficient N-tiles of the tensor-core DCT (0 = runtime p.nt8): a constant
 // trip count keeps the mma.sync sequence free of predicates / WARPSYNCs.
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8, typename SAMP>
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
+    const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
     constexpr bool PF = false;                              // register prefetch of the next pair: measured, no gain
     typedef FftGeom<NFFT> G;
     constexpr int NJ = JHI - JLO;
@@ -241,8 +253,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
         RawFrame<FAM, NJ> rawA, rawB;
         FramePos pA = frame_pos(2 * hw, nf, p.T, p.t_magic, p.cpc), pB = frame_pos(2 * hw + 1, nf, p.T, p.t_magic, p.cpc);
         if (PF && (hw & ~1) < npairs) {
-            fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-            fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
+            fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+            fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
         }
 
         for (int it = 0; it < rounds; ++it) {
@@ -253,8 +265,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 if (!PF) {
                     pA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc);
                     pB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
-                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-                    fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
+                    fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+                    fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
                 }
                 const FramePos cA = pA, cB = pB;
                 C2 v[G::V];
@@ -282,8 +294,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     pA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc);
                     pB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
                     if (((it + 1) * HW + (hw & ~1)) < npairs) {
-                        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-                        fetch_frame<FAM, JLO, JHI>(p, p.pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
+                        fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
+                        fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
                     }
                 }
 

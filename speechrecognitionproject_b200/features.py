@@ -130,19 +130,24 @@ def launch_count() -> int:
 # under torch.no_grad(), model_mfcc_bgru.py:29)
 # ------------------------------------------------------------------------------------
 def _prep(x: torch.Tensor) -> torch.Tensor:
-    if x.dtype != torch.float32:
-        raise TypeError(f"PCM must be float32 (dataset.py:117), got {x.dtype}")
+    if x.dtype not in (torch.float32, torch.int16):
+        raise TypeError(f"PCM must be float32 (dataset.py:117) or int16 (the wav's own type, dataset.py:103), got {x.dtype}")
     if x.dim() != 2:
         raise ValueError("expected a [n_clips, n_samples] tensor")
-    if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) % 2) or x.data_ptr() % 8:
+    pair = 2 * x.element_size()                    # rows aligned to a sample pair
+    if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) % 2) or x.data_ptr() % pair:
         x = x.contiguous()
-        if x.data_ptr() % 8:                       # odd-offset view of a larger buffer
+        if x.data_ptr() % pair:                    # odd-offset view of a larger buffer
             x = x.clone()
     return x
 
 
+def _suffix(x: torch.Tensor) -> str:
+    return "i16" if x.dtype == torch.int16 else "f32"
+
+
 def _run_device(fam: str, cp, x: torch.Tensor, out: torch.Tensor) -> None:
-    fn = getattr(_lib.lib(), f"srfe_{fam}_f32")
+    fn = getattr(_lib.lib(), f"srfe_{fam}_{_suffix(x)}")
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         stride = x.stride(0) if x.size(0) > 1 else x.size(1)
@@ -164,7 +169,7 @@ def _spec_op(pcm: torch.Tensor, fs: int, nperseg: int, noverlap: int, take_log: 
 def _(pcm, fs, nperseg, noverlap, take_log, eps, layout):
     t = (pcm.size(1) - noverlap) // (nperseg - noverlap)
     f = nperseg // 2 + 1
-    return pcm.new_empty((pcm.size(0), f, t) if layout == LAYOUT_FT else (pcm.size(0), t, f))
+    return pcm.new_empty((pcm.size(0), f, t) if layout == LAYOUT_FT else (pcm.size(0), t, f), dtype=torch.float32)
 
 
 @torch.library.custom_op("srfe::fbank", mutates_args=(), device_types="cuda")
@@ -181,7 +186,7 @@ def _fbank_op(pcm: torch.Tensor, fs: int, frame_len: int, frame_step: int, nfft:
 @_fbank_op.register_fake
 def _(pcm, fs, frame_len, frame_step, nfft, preemph, nfilt):
     t = -(-abs(pcm.size(1) - frame_len) // frame_step)
-    return pcm.new_empty((pcm.size(0), t, nfilt))
+    return pcm.new_empty((pcm.size(0), t, nfilt), dtype=torch.float32)
 
 
 @torch.library.custom_op("srfe::mfcc", mutates_args=(), device_types="cuda")
@@ -199,7 +204,7 @@ def _mfcc_op(pcm: torch.Tensor, sr: int, n_fft: int, win_length: int, hop: int, 
 def _(pcm, sr, n_fft, win_length, hop, n_mels, fmin, fmax, n_mfcc, n_deltas, top_db, amin, layout):
     t = 1 + pcm.size(1) // hop
     r = (1 + n_deltas) * n_mfcc
-    return pcm.new_empty((pcm.size(0), r, t) if layout == LAYOUT_FT else (pcm.size(0), t, r))
+    return pcm.new_empty((pcm.size(0), r, t) if layout == LAYOUT_FT else (pcm.size(0), t, r), dtype=torch.float32)
 
 
 # ------------------------------------------------------------------------------------
@@ -211,7 +216,7 @@ def _run_host(fam: str, cp, x: torch.Tensor, shape: tuple[int, int], device: Opt
     dev = torch.cuda.current_device() if device is None else device
     out = torch.empty((x.size(0),) + shape, dtype=torch.float32, pin_memory=x.is_pinned())
     stride = x.stride(0) if x.size(0) > 1 else x.size(1)
-    fn = getattr(_lib.lib(), f"srfe_{fam}_host_f32")
+    fn = getattr(_lib.lib(), f"srfe_{fam}_host_{_suffix(x)}")
     _lib.check(fn(x.data_ptr(), x.size(0), x.size(1), stride, C.byref(cp), out.data_ptr(), dev))
     return out
 

@@ -326,3 +326,22 @@ def test_large_batch_properties(srfe_lib):
         for i in (0, 7, 2048, 4095):
             assert torch.equal(fn(x[i:i + 1], p)[0], y[i])
     assert torch.allclose(S.mfcc(x[2048:2049], S.R_MFCC)[0, 0], torch.tensor(-100.0 * 128 ** 0.5, device="cuda"), atol=1e-3)
+
+
+def test_int16_ingest_bit_identical(srfe_lib, corpus):
+    """int16 PCM (the wav's own type, dataset.py:103) converted on load inside the kernel gives exactly the
+    features of its float32 copy (dataset.py:117) -- device and host entry points, every family."""
+    xi = torch.from_numpy(np.round(corpus).clip(-32768, 32767).astype(np.int16))
+    xf = xi.float()
+    for fn, p in ((S.spec, S.R_SPEC), (S.spec, replace(S.C_SPEC, layout="tf")), (S.fbank, S.R_FBANK), (S.fbank, S.C_FBANK),
+                  (S.mfcc, S.R_MFCC), (S.mfcc, S.C_MFCC), (S.mfcc, GENERIC_MFCC[3])):
+        a = fn(xf.cuda(), p)
+        b = fn(xi.cuda(), p)
+        assert b.dtype == torch.float32 and torch.equal(a, b)
+        c = fn(xi, p)                                   # host entry point, int16 H2D
+        assert not c.is_cuda and torch.equal(a.cpu(), c)
+    odd = torch.zeros(4, 16001, dtype=torch.int16)
+    odd[:, 1:] = xi[:4]
+    assert torch.equal(S.mfcc(odd[:, 1:].cuda()), S.mfcc(xf[:4].cuda()))      # misaligned view -> copied
+    with pytest.raises(TypeError):
+        S.mfcc(xi.to(torch.int32).cuda())
