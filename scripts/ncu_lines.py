@@ -5,8 +5,17 @@ src_csv, so = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 rows = list(csv.reader(open(src_csv)))
 kname = rows[0][1]
-m = re.search(r"srfe_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(unsigned int\)(\d+)>", kname)
-mangled = "srfe_kernelILi%sELi%sELi%sELi%sELi%sELj%sEE" % m.groups()
+import itertools
+def mangle(kname):
+    # srfe_kernel<(int)512, (int)2, ..., (unsigned int)41984, (int)5, short> -> Itanium template-args fragment
+    args = re.search(r"srfe_kernel<(.*)>\(", kname).group(1).split(", ")
+    out = ""
+    for a in args:
+        m = re.match(r"\((unsigned int|int|bool)\)(\d+)", a)
+        if m: out += "L" + {"int": "i", "unsigned int": "j", "bool": "b"}[m.group(1)] + m.group(2) + "E"
+        else: out += {"float": "f", "short": "s"}[a]
+    return "srfe_kernelI" + out + "E"
+mangled = mangle(kname)
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]; body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
 ci = {h: i for i, h in enumerate(hdr)}

@@ -286,7 +286,7 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
     c->dtab_off = c->ctile_off = blob;
     if (e->family == FAM_MFCC) {
         tile = align16((kp.T + 1) * kp.tile_stride * 4 + kp.T * 4);
-        const int TC = kp.T + 1 + (kp.T & 1);
+        const int TC = kp.T + 2;                                     // upper bound of the kernel's row stride
         const int cstat = align16(kp.n_mfcc * TC * 4), call = (1 + kp.n_deltas) * kp.n_mfcc * TC * 4;
         dtab = kp.use_mma ? kp.nt8 * 8 * ((kp.n_filt / 8) * 4 + 4) * 16 : 0;   // float4 {hi pair, lo pair} per (row, k-step, q)
         if (dtab && env_int("SRFE_DTAB_RESIDENT", 1) && blob + std::max(scratch, cstat) + tile + dtab <= budget &&

@@ -472,14 +472,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
             if ((tid & 31) == 0) s_red[tid >> 5] = run_max;
             __syncthreads();
-            float gmax = s_red[0];
-            for (int i = 1; i < (nthr >> 5); ++i) gmax = fmaxf(gmax, s_red[i]);
+            float gmax = (lane < (nthr >> 5)) ? s_red[lane] : -CUDART_INF_F;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
             const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
             // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
             //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
             // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
             // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
-            const int TC = p.T + 1 + (p.T & 1);              // odd row stride of the coefficient tile
+            // coefficient tile [row][TC]: FT output = the tile itself (TC = T, flat vector copy); TF output reads
+            // it transposed, so an odd stride keeps those reads conflict-free
+            const int TC = (p.layout == SRFE_LAYOUT_FT) ? p.T : p.T + 1 + (p.T & 1);
             const int warp = tid >> 5, nwarps = nthr >> 5;
             float* ctile = reinterpret_cast<float*>(smem + p.sm_ctile);
             if (p.use_mma) {
@@ -611,10 +614,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const int R = (1 + p.n_deltas) * p.n_mfcc;
             float* oc = p.out + (long long)clip0 * R * p.T;
             if (p.layout == SRFE_LAYOUT_FT) {
-                for (int r = warp; r < R; r += nwarps) {
-                    float* orow = oc + r * p.T;
-                    const float* crow = ctile + r * TC;
-                    for (int t = lane; t < p.T; t += 32) orow[t] = crow[t];
+                const int n = R * p.T;                       // the clip's features are one contiguous block
+                if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(oc) & 15) == 0)) {
+                    const float4* c4 = reinterpret_cast<const float4*>(ctile);
+                    float4* o4 = reinterpret_cast<float4*>(oc);
+                    for (int i = tid; i < (n >> 2); i += nthr) o4[i] = c4[i];
+                } else {
+                    for (int i = tid; i < n; i += nthr) oc[i] = ctile[i];
                 }
             } else {
                 for (int t = warp; t < p.T; t += nwarps) {
