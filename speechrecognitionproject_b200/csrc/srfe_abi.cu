@@ -326,7 +326,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
     const int per_sm = 228 * 1024;                                   // B200: 228 KB per SM, 1 KB reserved per CTA
     for (int ctas = 1; ctas <= 2; ++ctas) {
         const int budget = std::min(di.smem_optin, per_sm / ctas - 1024);
-        for (int warps = (ctas == 1 ? 8 : 4); warps <= (ctas == 1 ? 16 : 8); ++warps) {
+        for (int warps = (ctas == 1 ? 8 : 4); warps <= (ctas == 1 ? kMaxThreads / 32 : kMaxThreads / 64); ++warps) {
             Config pl{};
             const int smem = smem_plan(e, kp, warps, budget, &pl);
             if (smem < 0 || smem > budget) continue;
@@ -337,7 +337,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 // measured on B200 (scripts/tune.py): two co-resident CTAs overlap their phases and beat one
                 // larger CTA with more warps; the MFCC epilogue wants every warp to own exactly one DCT task
                 double score = (double)nf / (double)(rounds * per_round);
-                score *= 0.70 + 0.30 * std::min(16, ctas * warps) / 16.0;
+                score *= 0.70 + 0.30 * std::min(kMaxThreads / 32, ctas * warps) / (double)(kMaxThreads / 32);
                 if (ctas == 1) score *= 0.80;
                 score *= 1.0 - 0.004 * (cpc - 1);
                 if (e->family == FAM_MFCC && kp.use_mma) {
@@ -353,7 +353,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
     // developer overrides (tuning only)
     const int ow = env_int("SRFE_WARPS", 0), oc = env_int("SRFE_CTAS", 0), op = env_int("SRFE_CPC", 0);
     if (ow > 0 || oc > 0 || op > 0) {
-        const int w_ = ow > 0 ? std::min(16, std::max(1, ow)) : bc.warps;
+        const int w_ = ow > 0 ? std::min(kMaxThreads / 32, std::max(1, ow)) : bc.warps;
         const int c_ = oc > 0 ? std::min(8, std::max(1, oc)) : bc.ctas;
         const int p_ = (op > 0 && cpc_max > 1) ? op : bc.cpc;
         const int budget = std::min(di.smem_optin, per_sm / c_ - 1024);
@@ -382,6 +382,7 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     kp.sm_ctile = cfg.ctile_off;
     kp.dtab_resident = cfg.dtab_resident;
     kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
+    kp.sw_prefetch = env_int("SRFE_SWPF", 0);                        // measured: no effect (loads are not the limiter)
     kp.dct_ksplit = 1;
     if (e->family == FAM_MFCC && kp.use_mma) kp.dct_ksplit = dct_ksplit_for(kp, cfg.warps);   // spread the DCT over the warps
     const int smem = cfg.smem;

@@ -34,7 +34,7 @@ namespace srfe {
 
 enum Family { FAM_SPEC = 0, FAM_FBANK = 1, FAM_MFCC = 2 };
 
-constexpr int kMaxThreads = 512;       // <= 16 warps = 32 half-warps (64 frames in flight) per CTA
+constexpr int kMaxThreads = 512;       // <= 16 warps per CTA at 128 registers (640 threads / 96 regs measured slower)
 
 struct KParams {
     const void* pcm;                   // float32 or int16 samples (kernel template parameter SAMP)
@@ -44,6 +44,7 @@ struct KParams {
     int T, hop, start0;
     int cpc, n_groups;                 // clips per group, number of groups
     unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
+    int sw_prefetch;                   // issue prefetch.global.L1 for the next frame pair
     int sm_ctile, dct_ksplit;          // coefficient tile offset; K split of the DCT over warps (1, 2 or 4)
     int sm_dtab, dtab_resident;        // tensor-core DCT: pre-split (hi, lo) table, loaded once per CTA when it fits
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
@@ -91,6 +92,18 @@ __device__ __forceinline__ float edge_sample(const KParams& p, const S* __restri
         return __fsub_rn(ld1<S>(x + idx), __fmul_rn(p.preemph, prev));   // model_fbanks_cnn.py:20 (float32)
     }
     return (idx >= 0 && idx < p.n_samples) ? ld1<S>(x + idx) : 0.f;
+}
+
+// software prefetch of a frame's cache lines (no registers held): lane l touches line l (and l + 16)
+template <int NFFT, typename S>
+__device__ __forceinline__ void prefetch_frame(const S* __restrict__ x, int base, int n_samples, int l) {
+    constexpr int LINES = (NFFT * (int)sizeof(S) + 127) / 128 + 1;      // + 1: frames start mid-line in general
+    const int lo = max(base, 0), hi = min(base + NFFT, n_samples) - 1;
+#pragma unroll
+    for (int i = 0; i < (LINES + 15) / 16; ++i) {
+        const int idx = lo + (l + 16 * i) * (128 / (int)sizeof(S));
+        if (idx <= hi) asm volatile("prefetch.global.L1 [%0];" :: "l"(x + idx));
+    }
 }
 
 template <int FAM, int NJ>
@@ -170,6 +183,27 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b
 // lg2.approx with flush-to-zero: no denormal guard code (arguments are bounded below by eps / amin)
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// ---- N = 512 untangle without the shared-memory round trip ----------------------------------------------
+// After pass 2 lane l holds v[k2] = Z[l + 16 k2].  The mirror of k = l + 16 r (r < 8) is M - k = (16 - l) + 16 (15 - r):
+// register 15 - r of lane (16 - l) & 15 of the same half-warp -- 4 shuffles per packed value, 32 per lane, instead of a
+// 16 x STS.128 store of Z plus 33 x LDS.128 reads (24.5 KB of shared-memory traffic per 4-frame pass).  Lane 0 mirrors
+// onto itself with a different register index (Z[256 - 16 r] = v[16 - r]; r = 0: Z[0]); lane 8 mirrors onto itself exactly.
+__device__ __forceinline__ P2 fft_untangle_512_shfl(int l, int lane, const C2* v, const FftTables& T, P2* pa, P2* pb) {
+    const int src = (lane & 16) | ((16 - l) & 15);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        C2 zm;
+        zm.re.lo = __shfl_sync(0xffffffffu, v[15 - r].re.lo, src);
+        zm.re.hi = __shfl_sync(0xffffffffu, v[15 - r].re.hi, src);
+        zm.im.lo = __shfl_sync(0xffffffffu, v[15 - r].im.lo, src);
+        zm.im.hi = __shfl_sync(0xffffffffu, v[15 - r].im.hi, src);
+        if (l == 0) zm = (r == 0) ? v[0] : v[(16 - r) & 15];
+        const cpx w = T.twu[l + 16 * r];
+        untangle_pair(v[r], zm, w.x, w.y, pa[r], pb[r]);
+    }
+    return pmul(bc(4.f), pfma(v[8].re, v[8].re, pmul(v[8].im, v[8].im)));      // bin M/2 (meaningful on lane 0)
+}
+
 struct KParams;
 // DCT-II rows -> shared memory, pre-split into TF32 (hi, lo) pairs for the 3xTF32 products
 // layout: float4 {hi(f), hi(f+4), lo(f), lo(f+4)} per (row, k-step, q), f = 8 ks + q: exactly the B fragments of
@@ -210,7 +244,7 @@ __device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int wa
 template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8, typename SAMP>
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
-    constexpr bool PF = false;                              // register prefetch of the next pair: measured, no gain
+    constexpr bool PF = false;                              // register prefetch of the next pair: spills at 128 regs, no gain at 168
     typedef FftGeom<NFFT> G;
     constexpr int NJ = JHI - JLO;
     constexpr int F = G::M + 1;
@@ -269,14 +303,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
                 }
                 const FramePos cA = pA, cB = pB;
+                if (!PF && p.sw_prefetch) {                 // warm L1/L2 with the half-warp's next pair
+                    const int qn = q + HW;
+                    const FramePos nA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc), nB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
+                    if (nA.ok) prefetch_frame<NFFT, SAMP>(pcm + (long long)(clip0 + nA.c) * p.clip_stride, p.start0 + nA.t * p.hop, p.n_samples, l);
+                    if (nB.ok) prefetch_frame<NFFT, SAMP>(pcm + (long long)(clip0 + nB.c) * p.clip_stride, p.start0 + nB.t * p.hop, p.n_samples, l);
+                }
                 C2 v[G::V];
                 window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
                 fft_phase1<NFFT>(v, l, xb, T);
                 __syncwarp();
                 if (NFFT == 512) {
                     fft_phase2_512(l, xb, v);
-                    __syncwarp();
-                    fft_store_z_512(l, v, xb);
+                    pmid = fft_untangle_512_shfl(l, lane, v, T, pa, pb);
                 } else {
                     fft_phase2_640(l, xb, v, T);
                     __syncwarp();
@@ -286,8 +325,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     __syncwarp();
                     fft_store_z_640(l, v, xb);
                 }
-                __syncwarp();
-                pmid = fft_untangle<NFFT>(l, xb, T, pa, pb);
+                if (NFFT != 512) {
+                    __syncwarp();
+                    pmid = fft_untangle<NFFT>(l, xb, T, pa, pb);
+                }
 
                 if (PF) {   // prefetch the half-warp's next pair while this one goes through its output stage
                     const int qn = q + HW;
