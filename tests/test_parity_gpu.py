@@ -345,3 +345,32 @@ def test_int16_ingest_bit_identical(srfe_lib, corpus):
     assert torch.equal(S.mfcc(odd[:, 1:].cuda()), S.mfcc(xf[:4].cuda()))      # misaligned view -> copied
     with pytest.raises(TypeError):
         S.mfcc(xi.to(torch.int32).cuda())
+
+
+def test_results_do_not_depend_on_launch_configuration(srfe_lib, corpus, monkeypatch):
+    """compute-sanitizer is closed on this pool; as a race / hazard screen every family is run under several launch
+    configurations (developer overrides SRFE_WARPS / SRFE_CTAS / SRFE_CPC) and repeatedly: SPEC and FBANK must be
+    bit-identical everywhere (no arithmetic depends on the configuration), MFCC bit-identical across repeats and equal
+    to ~1 ulp across configurations (the DCT's K split changes the summation order)."""
+    x = torch.from_numpy(np.concatenate([corpus, corpus[:7]])).cuda()        # 31 clips: ragged last group
+    cases = [(S.spec, S.R_SPEC), (S.spec, replace(S.C_SPEC, layout="tf")), (S.fbank, S.R_FBANK), (S.fbank, S.C_FBANK),
+             (S.mfcc, S.R_MFCC), (S.mfcc, S.C_MFCC_D2)]
+    configs = [None, (4, 2, 1), (8, 2, 4), (5, 2, 2), (9, 1, 1), (16, 1, 8), (13, 1, 2)]
+    for fn, p in cases:
+        for k in ("SRFE_WARPS", "SRFE_CTAS", "SRFE_CPC"):
+            monkeypatch.delenv(k, raising=False)
+        base = fn(x, p)
+        for cfg in configs:
+            if cfg is not None:
+                monkeypatch.setenv("SRFE_WARPS", str(cfg[0])); monkeypatch.setenv("SRFE_CTAS", str(cfg[1])); monkeypatch.setenv("SRFE_CPC", str(cfg[2]))
+            try:
+                y1 = fn(x, p)
+            except RuntimeError as e:                    # a forced configuration may not fit in shared memory
+                assert "SRFE_ERR_TOO_LARGE" in str(e)
+                continue
+            for _ in range(3):
+                assert torch.equal(fn(x, p), y1), f"non-deterministic: {type(p).__name__} cfg={cfg}"
+            if fn is S.mfcc:
+                torch.testing.assert_close(y1, base, rtol=0, atol=2e-4)
+            else:
+                assert torch.equal(y1, base), f"configuration-dependent result: {type(p).__name__} cfg={cfg}"
