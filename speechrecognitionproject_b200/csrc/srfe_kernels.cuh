@@ -204,6 +204,42 @@ __device__ __forceinline__ P2 fft_untangle_512_shfl(int l, int lane, const C2* v
     return pmul(bc(4.f), pfma(v[8].re, v[8].re, pmul(v[8].im, v[8].im)));      // bin M/2 (meaningful on lane 0)
 }
 
+// ---- N = 640 untangle through shuffles --------------------------------------------------------------------
+// After pass 3 lane (c = l & 3, b = l >> 2) holds v[4 i + kb] = Z[k1 + 20 k2], k1 = b + 4 i, k2 = c + 4 kb.  Each lane
+// takes its 10 bins with kb < 2 (k < 160) and needs the mirror M - k = (20 - k1) % 20 + 20 (15 - k2) [k1 != 0] or
+// 20 ((16 - k2) % 16) [k1 == 0]:
+//   b != 0          : lane (3 - c, 4 - b), register 19 - j                      (j = 4 i + kb)
+//   b == 0, i >= 1  : lane (3 - c, 0),     register 23 - j
+//   b == 0, i == 0  : lane ((4 - c) & 3, 0), register (c == 0 ? (4 - kb) & 3 : 3 - kb)
+// A b == 0 lane is only ever read by b == 0 lanes, so the sender picks the register by its own (b, c).
+// bin of slot r = 2 i + kb:  k = b + 4 i + 20 c + 80 kb.
+__device__ __forceinline__ int bin640(int l, int r) { return (l >> 2) + 4 * (r >> 1) + 20 * (l & 3) + 80 * (r & 1); }
+
+__device__ __forceinline__ P2 fft_untangle_640_shfl(int l, int lane, const C2* v, const FftTables& T, P2* pa, P2* pb) {
+    const int c = l & 3, b = l >> 2, hb = lane & 16;
+    const int src_hi = hb | (b != 0 ? (3 - c) + 4 * (4 - b) : (3 - c));      // slots with i >= 1
+    const int src_lo = hb | (b != 0 ? (3 - c) + 4 * (4 - b) : ((4 - c) & 3));    // slots with i == 0
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            const int j = 4 * i + kb, r = 2 * i + kb;
+            C2 snd;
+            if (i >= 1) snd = (b != 0) ? v[19 - j] : v[23 - j];
+            else        snd = (b != 0) ? v[19 - j] : ((c == 0) ? v[(4 - kb) & 3] : v[3 - kb]);
+            const int src = (i >= 1) ? src_hi : src_lo;
+            C2 zm;
+            zm.re.lo = __shfl_sync(0xffffffffu, snd.re.lo, src);
+            zm.re.hi = __shfl_sync(0xffffffffu, snd.re.hi, src);
+            zm.im.lo = __shfl_sync(0xffffffffu, snd.im.lo, src);
+            zm.im.hi = __shfl_sync(0xffffffffu, snd.im.hi, src);
+            const cpx w = T.twu[bin640(l, r)];
+            untangle_pair(v[j], zm, w.x, w.y, pa[r], pb[r]);
+        }
+    }
+    return pmul(bc(4.f), pfma(v[2].re, v[2].re, pmul(v[2].im, v[2].im)));      // bin 160 = lane 0, register (i = 0, kb = 2)
+}
+
 struct KParams;
 // DCT-II rows -> shared memory, pre-split into TF32 (hi, lo) pairs for the 3xTF32 products
 // layout: float4 {hi(f), hi(f+4), lo(f), lo(f+4)} per (row, k-step, q), f = 8 ks + q: exactly the B fragments of
@@ -322,13 +358,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     fft_scatter2_640(l, v, xb);
                     __syncwarp();
                     fft_phase3_640(l, xb, v);
-                    __syncwarp();
-                    fft_store_z_640(l, v, xb);
+                    pmid = fft_untangle_640_shfl(l, lane, v, T, pa, pb);
                 }
-                if (NFFT != 512) {
-                    __syncwarp();
-                    pmid = fft_untangle<NFFT>(l, xb, T, pa, pb);
-                }
+
+                // bin held in slot r of this lane (and its mirror M - k): natural stride-16 order for N = 512,
+                // the radix-4 order of bin640() for N = 640
+                auto kbin = [&](int r) { return NFFT == 512 ? l + 16 * r : bin640(l, r); };
 
                 if (PF) {   // prefetch the half-warp's next pair while this one goes through its output stage
                     const int qn = q + HW;
@@ -346,9 +381,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     if (p.layout == SRFE_LAYOUT_TF) {
                         float* rowA = p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * F;
                         float* rowB = p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * F;
+                        P2* pbuf = reinterpret_cast<P2*>(xb);       // N = 640 only: re-order through shared memory
 #pragma unroll
                         for (int r = 0; r < G::M / 32; ++r) {
-                            const int k = l + 16 * r;
+                            const int k = kbin(r);
                             const float sc = (r == 0 && l == 0) ? p.scale : s2;
                             float a0, a1, b0, b1;
                             if (p.take_log) {               // ln(S + eps) = ln2 * lg2(fma(P, scale, eps))
@@ -359,14 +395,36 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             } else {
                                 a0 = pa[r].lo * sc; a1 = pa[r].hi * sc; b0 = pb[r].lo * sc; b1 = pb[r].hi * sc;
                             }
-                            if (cA.ok) { rowA[k] = a0; rowA[G::M - k] = b0; }
-                            if (cB.ok) { rowB[k] = a1; rowB[G::M - k] = b1; }
+                            if (NFFT == 512) {              // lanes hold consecutive bins: store straight from registers
+                                if (cA.ok) { rowA[k] = a0; rowA[G::M - k] = b0; }
+                                if (cB.ok) { rowB[k] = a1; rowB[G::M - k] = b1; }
+                            } else {
+                                pbuf[k] = mkp(a0, a1);
+                                pbuf[G::M - k] = mkp(b0, b1);
+                            }
                         }
-                        if (l == 0) {
-                            float c0 = pmid.lo * s2, c1 = pmid.hi * s2;
-                            if (p.take_log) { c0 = 0.6931471805599453f * lg2_ftz(c0 + p.log_eps); c1 = 0.6931471805599453f * lg2_ftz(c1 + p.log_eps); }
-                            if (cA.ok) rowA[G::M / 2] = c0;
-                            if (cB.ok) rowB[G::M / 2] = c1;
+                        float c0 = pmid.lo * s2, c1 = pmid.hi * s2;
+                        if (p.take_log) { c0 = 0.6931471805599453f * lg2_ftz(c0 + p.log_eps); c1 = 0.6931471805599453f * lg2_ftz(c1 + p.log_eps); }
+                        if (NFFT == 512) {
+                            if (l == 0) {
+                                if (cA.ok) rowA[G::M / 2] = c0;
+                                if (cB.ok) rowB[G::M / 2] = c1;
+                            }
+                        } else {
+                            if (l == 0) pbuf[G::M / 2] = mkp(c0, c1);
+                            __syncwarp();
+#pragma unroll
+                            for (int r = 0; r < G::M / 16; ++r) {       // natural order: 64-byte runs per half-warp
+                                const P2 q2 = pbuf[l + 16 * r];
+                                if (cA.ok) rowA[l + 16 * r] = q2.lo;
+                                if (cB.ok) rowB[l + 16 * r] = q2.hi;
+                            }
+                            if (l == 0) {
+                                const P2 q2 = pbuf[G::M];
+                                if (cA.ok) rowA[G::M] = q2.lo;
+                                if (cB.ok) rowB[G::M] = q2.hi;
+                            }
+                            __syncwarp();
                         }
                     } else {
                         // FT: keep the scaled / logged values in registers; they go through a CTA-wide
@@ -395,7 +453,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < G::M / 32; ++r) {
-                        const int k = l + 16 * r;
+                        const int k = kbin(r);
                         pbuf[k] = pa[r];
                         pbuf[G::M - k] = pb[r];
                     }
@@ -487,7 +545,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     float* col = ft + 2 * hw;
 #pragma unroll
                     for (int r = 0; r < G::M / 32; ++r) {
-                        const int k = l + 16 * r;
+                        const int k = NFFT == 512 ? l + 16 * r : bin640(l, r);
                         col[k * RS] = pa[r].lo;            col[k * RS + 1] = pa[r].hi;
                         col[(G::M - k) * RS] = pb[r].lo;   col[(G::M - k) * RS + 1] = pb[r].hi;
                     }
