@@ -469,10 +469,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                         if (guard && m >= p.n_filt) return;
                         if (FAM == FAM_FBANK) {
                             float a = acc.lo, b = acc.hi;
-                            if (a == 0.f) a = 2.220446049250313e-16f;                  // model_fbanks_cnn.py:61
-                            if (b == 0.f) b = 2.220446049250313e-16f;
-                            if (cA.ok) orowA[m] = 6.020599913279624f * __log2f(a);      // 20 log10
-                            if (cB.ok) orowB[m] = 6.020599913279624f * __log2f(b);
+                            // model_fbanks_cnn.py:61: exact zeros -> eps; denormal sums are lifted to FLT_MIN so the
+                            // flush-to-zero log never returns -inf (far below any level the front end can resolve)
+                            a = (a == 0.f) ? 2.220446049250313e-16f : fmaxf(a, 1.17549435e-38f);
+                            b = (b == 0.f) ? 2.220446049250313e-16f : fmaxf(b, 1.17549435e-38f);
+                            if (cA.ok) orowA[m] = 6.020599913279624f * lg2_ftz(a);      // 20 log10
+                            if (cB.ok) orowB[m] = 6.020599913279624f * lg2_ftz(b);
                         } else {
                             const float da = 3.010299956639812f * lg2_ftz(fmaxf(acc.lo, p.amin));   // 10 log10
                             const float db = 3.010299956639812f * lg2_ftz(fmaxf(acc.hi, p.amin));
