@@ -3,6 +3,7 @@
 // the host-buffer entry points (H2D -> kernel -> D2H, chunked over two streams).
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -38,8 +39,9 @@ struct Entry {
     int family = 0;
     int blob_smem = 0;
     void* d_blob = nullptr;
-    void* d_dct = nullptr;
     void* d_dct_kf = nullptr;
+    void* d_dfold = nullptr;
+    int dfold_bytes = 0;
     int mel_ng = 0;             // ELL shape: groups and 2-bit run-length code (0 groups = not encodable)
     unsigned mel_code = 0;
     int n_bins = 0;
@@ -79,8 +81,7 @@ static void window_range(const std::vector<double>& w, int& lo, int& hi) {
     hi = (b + 2) & ~1;                                   // exclusive, rounded up to even
 }
 
-static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct_t,
-                  const std::vector<float>& dct_kf = std::vector<float>()) {
+static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct_kf = std::vector<float>()) {
     if (!dct_kf.empty()) {
         SRFE_CUDA(cudaMalloc(&e->d_dct_kf, dct_kf.size() * sizeof(float)));
         SRFE_CUDA(cudaMemcpy(e->d_dct_kf, dct_kf.data(), dct_kf.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -88,13 +89,8 @@ static int upload(Entry* e, const BlobBuilder& bb, const std::vector<float>& dct
     }
     SRFE_CUDA(cudaMalloc(&e->d_blob, bb.data.size()));
     SRFE_CUDA(cudaMemcpy(e->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
-    if (!dct_t.empty()) {
-        SRFE_CUDA(cudaMalloc(&e->d_dct, dct_t.size() * sizeof(float)));
-        SRFE_CUDA(cudaMemcpy(e->d_dct, dct_t.data(), dct_t.size() * sizeof(float), cudaMemcpyHostToDevice));
-    }
     e->kp.blob = (const unsigned char*)e->d_blob;
     e->kp.blob_bytes = (int)bb.data.size();
-    e->kp.dct_t = (const float*)e->d_dct;
     e->blob_smem = (int)bb.data.size();
     return SRFE_OK;
 }
@@ -169,7 +165,7 @@ static int build_entry(const srfe_spec_params& p, Entry* e) {
     e->kp.log_eps = p.log_eps;
     e->kp.take_log = p.take_log;
     e->kp.layout = p.layout;
-    return upload(e, bb, {});
+    return upload(e, bb);
 }
 
 static int build_entry(const srfe_fbank_params& p, Entry* e) {
@@ -187,7 +183,7 @@ static int build_entry(const srfe_fbank_params& p, Entry* e) {
     e->kp.start0 = 0;
     e->kp.preemph = p.preemph;
     e->kp.layout = SRFE_LAYOUT_TF;
-    return upload(e, bb, {});
+    return upload(e, bb);
 }
 
 static int build_entry(const srfe_mfcc_params& p, Entry* e) {
@@ -210,21 +206,31 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.top_db = p.top_db;
     e->kp.amin = p.amin;
     e->kp.layout = p.layout;
-    e->kp.use_mma = (p.n_mels % 8 == 0) ? 1 : 0;
-    e->kp.nt8 = (p.n_mfcc + 7) / 8;
-    // tensor-core path: stride = 4 (mod 32) makes the mma fragment loads conflict-free;
-    // CUDA-core path: odd stride for conflict-free column reads
-    e->kp.tile_stride = e->kp.use_mma ? p.n_mels + 4 : (p.n_mels | 1);
+    e->kp.tile_stride = p.n_mels | 1;                                  // P2 units, odd: conflict-free pair-row reads
     double rs0 = 0.0;
     for (int f = 0; f < p.n_mels; ++f) rs0 += dct[f];
     e->kp.dct_row0_sum = (float)rs0;                                   // = sqrt(n_mels)
-    std::vector<float> dct_t((size_t)p.n_mels * e->kp.n_mfcc_pad, 0.f);
-    for (int k = 0; k < p.n_mfcc; ++k)
-        for (int f = 0; f < p.n_mels; ++f) dct_t[(size_t)f * e->kp.n_mfcc_pad + k] = (float)dct[(size_t)k * p.n_mels + f];
-    std::vector<float> dct_kf((size_t)e->kp.nt8 * 8 * p.n_mels, 0.f);
-    for (int k = 0; k < p.n_mfcc; ++k)
-        for (int f = 0; f < p.n_mels; ++f) dct_kf[(size_t)k * p.n_mels + f] = (float)dct[(size_t)k * p.n_mels + f];
-    return upload(e, bb, dct_t, dct_kf);
+    // folded DCT table (even n_mels): [parity][f < n/2][NJ], coefficient k = 2 j + parity, NJ padded to 4s
+    e->kp.dct_fold = (p.n_mels % 2 == 0 && p.n_mels >= 4 && (p.n_mels / 2) % 2 == 0) ? 1 : 0;
+    if (e->kp.dct_fold) {
+        // [parity][f < n/2][NJ] floats, coefficient k = 2 j + parity at column j, NJ padded to a multiple of 4
+        const int half = p.n_mels / 2, ne = (p.n_mfcc + 1) / 2;
+        const int NJ = ((ne + 3) / 4) * 4;
+        std::vector<float> fold((size_t)2 * half * NJ, 0.f);
+        for (int k = 0; k < p.n_mfcc; ++k)
+            for (int f = 0; f < half; ++f)
+                fold[((size_t)(k & 1) * half + f) * NJ + (k >> 1)] = (float)dct[(size_t)k * p.n_mels + f];
+        e->kp.dct_nj = NJ;
+        e->dfold_bytes = (int)fold.size() * 4;
+        e->kp.off_dfold = bb.add(fold.data(), fold.size() * 4);      // last blob item: can be left out of the smem copy
+        if (cudaMalloc(&e->d_dfold, fold.size() * 4) != cudaSuccess ||
+            cudaMemcpy(e->d_dfold, fold.data(), fold.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return cuda_fail(cudaGetLastError(), "dfold upload");
+        e->kp.dfold_g = (const float*)e->d_dfold;
+    }
+    std::vector<float> dct_kf((size_t)p.n_mfcc * p.n_mels);
+    for (size_t i = 0; i < dct_kf.size(); ++i) dct_kf[i] = (float)dct[i];
+    return upload(e, bb, dct_kf);
 }
 
 // ------------------------------------------------------------------------------
@@ -246,9 +252,9 @@ static int dev_info(DevInfo** out) {
     return SRFE_OK;
 }
 
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8, typename SAMP>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
 static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, NT8, SAMP>;
+    auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, SAMP>;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         int dev = 0;
@@ -266,54 +272,37 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
     return SRFE_OK;
 }
 
-struct Config { int warps, ctas, cpc, smem, scratch, tile, dtab_off, ctile_off, dtab_resident; };
+struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, dfold_global, blob; };
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// Shared-memory plan of a CTA with `warps` warps and up to `budget` bytes:
-//   [tables][FFT scratch][dB tile + dummy row + frame means][resident DCT table?]
-// The MFCC epilogue reuses the FFT scratch for the coefficient tile (and, when the pre-split DCT table
-// is not resident, for that table too); delta rows may spill into the (dead) dB tile.
+// Shared-memory plan of a CTA with `warps` warps:  [tables][FFT scratch][MFCC pair-row dB tile + pair means]
+// The MFCC epilogue reuses the FFT scratch for the coefficient tile; delta rows may spill into the (dead) dB tile.
 static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, Config* c) {
+    (void)budget;
     const int hw = 2 * warps;
-    const int blob = align16(e->blob_smem);
+    const bool dg = e->family == FAM_MFCC && e->dfold_bytes > 0 && env_int("SRFE_DFOLD_GLOBAL", 0);
+    const int blob = align16(e->blob_smem - (dg ? e->dfold_bytes : 0));   // the folded DCT table is the blob's tail
+    c->dfold_global = dg ? 1 : 0;
+    c->blob = blob;
     int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 16;
-    int tile = 0, dtab = 0;
-    c->dtab_resident = 0;
-    c->dtab_off = c->ctile_off = blob;
+    int tile = 0;
+    c->ctile_off = blob;
     if (e->family == FAM_MFCC) {
-        tile = align16((kp.T + 1) * kp.tile_stride * 4 + kp.T * 4);
+        const int npairs = (kp.T + 1) / 2;
+        tile = align16((npairs + 1) * kp.tile_stride * 8 + (npairs + 1) * 8);
         const int TC = kp.T + 2;                                     // upper bound of the kernel's row stride
         const int cstat = align16(kp.n_mfcc * TC * 4), call = (1 + kp.n_deltas) * kp.n_mfcc * TC * 4;
-        dtab = kp.use_mma ? kp.nt8 * 8 * ((kp.n_filt / 8) * 4 + 4) * 16 : 0;   // float4 {hi pair, lo pair} per (row, k-step, q)
-        if (dtab && env_int("SRFE_DTAB_RESIDENT", 1) && blob + std::max(scratch, cstat) + tile + dtab <= budget &&
-            call <= std::max(scratch, cstat) + tile) {
-            c->dtab_resident = 1;                                    // own region after the tile
-            scratch = std::max(scratch, cstat);
-            c->dtab_off = blob + scratch + tile;
-            c->ctile_off = blob;
-        } else {
-            if (dtab + cstat > scratch) scratch = align16(dtab + cstat);
-            if (dtab + call > scratch + tile) return -1;
-            c->dtab_off = blob;
-            c->ctile_off = blob + dtab;
-            dtab = 0;
-        }
+        if (cstat > scratch) scratch = cstat;
+        if (call > scratch + tile) return -1;
     }
     c->scratch = scratch;
     c->tile = tile;
-    c->smem = blob + scratch + tile + dtab;
+    c->smem = blob + scratch + tile;
     return c->smem;
-}
-
-// K split of the tensor-core DCT: 2 when that still gives every warp at most one (M-tile, K-half) task
-// (2 partial sums added with shared-memory atomics: commutative, so the result stays deterministic)
-static int dct_ksplit_for(const KParams& kp, int warps) {
-    const int mtiles = (kp.T + 15) / 16, ksteps = kp.n_filt / 8;
-    return (ksteps % 2 == 0 && mtiles * 2 <= warps) ? 2 : 1;
 }
 
 // Warps per CTA, CTAs per SM and clips per group: fill whole rounds of 4*warps frames, keep as many
@@ -334,17 +323,13 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 if (cpc > 1 && cpc > kp.n_clips) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
-                // measured on B200 (scripts/tune.py): two co-resident CTAs overlap their phases and beat one
-                // larger CTA with more warps; the MFCC epilogue wants every warp to own exactly one DCT task
+                // Fitted to scripts/tune.py sweeps on the B200: throughput ~ round efficiency x (resident warps - 2.3)^0.8;
+                // for MFCC (CTA barriers + serial epilogue) two co-resident CTAs are worth ~1.6x one CTA at equal warps,
+                // for SPEC / FBANK (no barriers) the CTA count does not matter.
                 double score = (double)nf / (double)(rounds * per_round);
-                score *= 0.70 + 0.30 * std::min(kMaxThreads / 32, ctas * warps) / (double)(kMaxThreads / 32);
-                if (ctas == 1) score *= 0.80;
+                score *= std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
+                if (ctas == 2) score *= (e->family == FAM_MFCC) ? 1.6 : 1.02;
                 score *= 1.0 - 0.004 * (cpc - 1);
-                if (e->family == FAM_MFCC && kp.use_mma) {
-                    const int tasks = ((kp.T + 15) / 16) * dct_ksplit_for(kp, warps);
-                    const int waves = (tasks + warps - 1) / warps;
-                    score *= 0.80 + 0.20 * (double)tasks / (double)(waves * warps);
-                }
                 if (score > best + 1e-9) { best = score; bc = pl; bc.warps = warps; bc.ctas = ctas; bc.cpc = cpc; }
             }
         }
@@ -376,15 +361,14 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     if (rc != SRFE_OK) return rc;
     kp.cpc = cfg.cpc;
     kp.n_groups = (kp.n_clips + cfg.cpc - 1) / cfg.cpc;
-    kp.sm_scratch = align16(e->blob_smem);
+    kp.sm_scratch = cfg.blob;
     kp.sm_tile = kp.sm_scratch + cfg.scratch;
-    kp.sm_dtab = cfg.dtab_off;
+    kp.dfold_global = cfg.dfold_global;
+    kp.blob_bytes = cfg.blob;                                        // smem copy stops before the table when it stays global
     kp.sm_ctile = cfg.ctile_off;
-    kp.dtab_resident = cfg.dtab_resident;
     kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
     kp.sw_prefetch = env_int("SRFE_SWPF", 0);                        // measured: no effect (loads are not the limiter)
-    kp.dct_ksplit = 1;
-    if (e->family == FAM_MFCC && kp.use_mma) kp.dct_ksplit = dct_ksplit_for(kp, cfg.warps);   // spread the DCT over the warps
+    kp.debug = env_int("SRFE_DEBUG", 0);
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
     // Curated instantiation list.  Window extents (units of 32 samples) and the preset shapes of the mel
@@ -393,32 +377,32 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     //   mel {8 groups, 0xe500}: 128 Slaney mels @ n_fft 640
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
     const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
-#define SRFE_GO(N, FAM, JLO, JHI, NG, CODE, NT8)                                                                 \
-    return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, NT8, short>(kp, grid, threads, smem, st)                   \
-               : launch_k<N, FAM, JLO, JHI, NG, CODE, NT8, float>(kp, grid, threads, smem, st)
+#define SRFE_GO(N, FAM, JLO, JHI, NG, CODE)                                                                      \
+    return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, short>(kp, grid, threads, smem, st)                        \
+               : launch_k<N, FAM, JLO, JHI, NG, CODE, float>(kp, grid, threads, smem, st)
     if (e->n_fft == 512) {
         switch (e->family) {
-            case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16, 0, 0u, 0);
+            case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16, 0, 0u);
             case FAM_FBANK:
                 if (jlo == 0 && jhi <= 13) {
-                    if (a400) SRFE_GO(512, FAM_FBANK, 0, 13, 8, 0xa400u, 0);
-                    SRFE_GO(512, FAM_FBANK, 0, 13, 0, 0u, 0);
+                    if (a400) SRFE_GO(512, FAM_FBANK, 0, 13, 8, 0xa400u);
+                    SRFE_GO(512, FAM_FBANK, 0, 13, 0, 0u);
                 }
-                SRFE_GO(512, FAM_FBANK, 0, 16, 0, 0u, 0);
+                SRFE_GO(512, FAM_FBANK, 0, 16, 0, 0u);
             default:
                 if (jlo >= 1 && jhi <= 15) {
-                    if (a400 && kp.use_mma && kp.nt8 == 5) SRFE_GO(512, FAM_MFCC, 1, 15, 8, 0xa400u, 5);
-                    SRFE_GO(512, FAM_MFCC, 1, 15, 0, 0u, 0);
+                    if (a400) SRFE_GO(512, FAM_MFCC, 1, 15, 8, 0xa400u);
+                    SRFE_GO(512, FAM_MFCC, 1, 15, 0, 0u);
                 }
-                SRFE_GO(512, FAM_MFCC, 0, 16, 0, 0u, 0);
+                SRFE_GO(512, FAM_MFCC, 0, 16, 0, 0u);
         }
     } else {
         switch (e->family) {
-            case FAM_SPEC: SRFE_GO(640, FAM_SPEC, 0, 20, 0, 0u, 0);
-            case FAM_FBANK: SRFE_GO(640, FAM_FBANK, 0, 20, 0, 0u, 0);
+            case FAM_SPEC: SRFE_GO(640, FAM_SPEC, 0, 20, 0, 0u);
+            case FAM_FBANK: SRFE_GO(640, FAM_FBANK, 0, 20, 0, 0u);
             default:
-                if (e500 && kp.use_mma && kp.nt8 == 2) SRFE_GO(640, FAM_MFCC, 0, 20, 8, 0xe500u, 2);
-                SRFE_GO(640, FAM_MFCC, 0, 20, 0, 0u, 0);
+                if (e500) SRFE_GO(640, FAM_MFCC, 0, 20, 8, 0xe500u);
+                SRFE_GO(640, FAM_MFCC, 0, 20, 0, 0u);
         }
     }
 #undef SRFE_GO

@@ -19,9 +19,9 @@
 //     -> SPEC : scale, ln(. + eps)              -> global (TF) or per-warp 4-frame staging (FT)
 //        FBANK: sparse triangle sums (uniform-trip ELL), 20 log10 -> global [T][nfilt]
 //        MFCC : sparse Slaney sums, 10 log10    -> per-clip dB tile in shared memory
-//   MFCC epilogue (CTA barrier): clip max -> top_db clamp -> DCT-II on tensor cores
-//   (3xTF32 mma.sync) -> np.gradient deltas -> coalesced store.  Only final features
-//   reach HBM.
+//   MFCC epilogue (CTA barrier): clip max -> top_db clamp -> DCT-II (packed FFMA2 with the
+//   even/odd symmetry fold; the legacy mma.sync TF32 path measured slower at fp32 accuracy)
+//   -> np.gradient deltas -> coalesced store.  Only final features reach HBM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -45,8 +45,8 @@ struct KParams {
     int cpc, n_groups;                 // clips per group, number of groups
     unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
     int sw_prefetch;                   // issue prefetch.global.L1 for the next frame pair
-    int sm_ctile, dct_ksplit;          // coefficient tile offset; K split of the DCT over warps (1, 2 or 4)
-    int sm_dtab, dtab_resident;        // tensor-core DCT: pre-split (hi, lo) table, loaded once per CTA when it fits
+    int debug;                         // developer switches (timing experiments only): 1 = skip the MFCC epilogue
+    int sm_ctile;                      // coefficient tile offset (aliases the FFT scratch)
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
     int blob_bytes;                    // multiple of 16
     int off_win, off_tw1, off_twu, off_tw16;
@@ -57,11 +57,11 @@ struct KParams {
     float preemph;
     int n_mfcc, n_mfcc_pad, n_deltas;
     float top_db, amin, dct_row0_sum;
-    const float* dct_t;                // global [n_mels][n_mfcc_pad]   (CUDA-core DCT path)
-    const float* dct_kf;               // global [nt8*8][n_mels], zero-padded rows (tensor-core DCT path)
-    int use_mma, nt8;                  // DCT on mma.sync 3xTF32 when n_mels % 8 == 0; nt8 = ceil(n_mfcc / 8)
+    const float* dct_kf;               // global [n_mfcc][n_mels] DCT-II rows (generic path, odd n_mels)
+    const float* dfold_g; int dfold_global;   // the same table in global memory
+    int dct_fold, dct_nj, off_dfold;   // folded DCT table in the blob: [parity][f < n/2][dct_nj] floats (dct_nj % 4 == 0)
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
-    int tile_stride;                   // MFCC dB tile row stride (floats)
+    int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
     int w_lo, w_hi;                    // non-zero extent of the window (informational)
 };
 
@@ -166,20 +166,6 @@ __device__ __forceinline__ void window_pair(const KParams& p, const RawFrame<FAM
     }
 }
 
-// --------------------------------------------------------------------------------
-// 3xTF32 tensor-core helper for the DCT epilogue (fp32-grade accuracy: the dropped
-// lo*lo term is ~2^-22 relative)
-// --------------------------------------------------------------------------------
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;         // round to nearest tf32: lo is signed, |lo| <= 2^-12 |x|
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // lg2.approx with flush-to-zero: no denormal guard code (arguments are bounded below by eps / amin)
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -240,12 +226,6 @@ __device__ __forceinline__ P2 fft_untangle_640_shfl(int l, int lane, const C2* v
     return pmul(bc(4.f), pfma(v[2].re, v[2].re, pmul(v[2].im, v[2].im)));      // bin 160 = lane 0, register (i = 0, kb = 2)
 }
 
-struct KParams;
-// DCT-II rows -> shared memory, pre-split into TF32 (hi, lo) pairs for the 3xTF32 products
-// layout: float4 {hi(f), hi(f+4), lo(f), lo(f+4)} per (row, k-step, q), f = 8 ks + q: exactly the B fragments of
-// mma.m16n8k8 for lane (g = row % 8, q); row stride (K/8)*4 + 4 float4 keeps the LDS.128 conflict-free
-__device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int warp, int nwarps, int lane);
-
 struct FramePos { int c, t; bool ok; };
 // flattened frame -> (clip in group, frame); division by T through a host-computed magic multiplier
 // (exact for f * T < 2^32); single-clip groups (MFCC) skip it altogether
@@ -258,16 +238,87 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
     return r;
 }
 
-__device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int warp, int nwarps, int lane) {
-    const int ksn = p.n_filt >> 3, RS4 = ksn * 4 + 4;
-    for (int row = warp; row < p.nt8 * 8; row += nwarps)
-        for (int e = lane; e < ksn * 4; e += 32) {
-            const int ks = e >> 2, q = e & 3;
-            uint32_t h0, l0, h1, l1;
-            split_tf32(__ldg(p.dct_kf + row * p.n_filt + 8 * ks + q), h0, l0);
-            split_tf32(__ldg(p.dct_kf + row * p.n_filt + 8 * ks + q + 4), h1, l1);
-            dtab[row * RS4 + e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+// --------------------------------------------------------------------------------
+// folded DCT-II on the FP32 pipe (see the epilogue comment in the kernel)
+//   warp task = (parity, block of 4 coefficients, chunk of 16 QL frame pairs): lane (fh, ql) takes the pairs
+//   ql, ql + 16, ... and half of the f range; per f one LDS.128 brings the 4 coefficients (broadcast) and QL LDS.64
+//   the pairs -> 4 QL FFMA2.  The two f halves are combined with one shuffle: no atomics, deterministic.
+//   Table layout: [parity][f < n/2][NJ] floats, NJ = coefficients per parity padded to a multiple of 4.
+//   (Measured alternatives, both slower: 5-coefficient blocks split over warps with shared-memory atomics; the table
+//   read through L1 from global memory to make room for a second CTA per SM.)
+// --------------------------------------------------------------------------------
+template <int QL>
+__device__ __forceinline__ void dct_fold_tasks(const KParams& p, const P2* tileP, const float* dfold, const P2* fmeanP,
+                                               float* ctile, float thr, int npairs, int TC, int warp, int nwarps, int lane) {
+    const int half = p.n_filt >> 1, NJ = p.dct_nj, TSP = p.tile_stride;
+    const int nblk = NJ >> 2, qchunks = (npairs + 16 * QL - 1) / (16 * QL);
+    const int fh = lane >> 4, ql = lane & 15, fspan = half >> 1;
+    for (int task = warp; task < 2 * nblk * qchunks; task += nwarps) {
+        const int qc = task % qchunks, kb = task / qchunks;
+        const int par = kb / nblk, blk = kb - par * nblk;
+        const int f0 = fh * fspan, f1 = (fh == 0) ? fspan : half;
+        const P2* xr[QL];
+#pragma unroll
+        for (int i = 0; i < QL; ++i) {
+            const int q = min(qc * 16 * QL + ql + 16 * i, npairs - 1);
+            xr[i] = tileP + q * TSP + (par == 0 ? f0 : p.n_filt - 1 - f0);       // even k: s[f] upwards; odd k: d[n-1-f] downwards
         }
+        const float* dr = dfold + (par * half + f0) * NJ + 4 * blk;
+        P2 acc[QL][4];
+#pragma unroll
+        for (int i = 0; i < QL; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = bc(0.f); }
+        if (par == 0) {
+#pragma unroll 2
+            for (int f = 0; f < f1 - f0; ++f) {
+                const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
+#pragma unroll
+                for (int i = 0; i < QL; ++i) {
+                    const P2 x = xr[i][f];
+                    acc[i][0] = pfma(x, bc(d.x), acc[i][0]); acc[i][1] = pfma(x, bc(d.y), acc[i][1]);
+                    acc[i][2] = pfma(x, bc(d.z), acc[i][2]); acc[i][3] = pfma(x, bc(d.w), acc[i][3]);
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int f = 0; f < f1 - f0; ++f) {
+                const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
+#pragma unroll
+                for (int i = 0; i < QL; ++i) {
+                    const P2 x = xr[i][-f];
+                    acc[i][0] = pfma(x, bc(d.x), acc[i][0]); acc[i][1] = pfma(x, bc(d.y), acc[i][1]);
+                    acc[i][2] = pfma(x, bc(d.z), acc[i][2]); acc[i][3] = pfma(x, bc(d.w), acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < QL; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[i][j].lo += __shfl_xor_sync(0xffffffffu, acc[i][j].lo, 16);
+                acc[i][j].hi += __shfl_xor_sync(0xffffffffu, acc[i][j].hi, 16);
+            }
+        if (fh == 0) {
+#pragma unroll
+            for (int i = 0; i < QL; ++i) {
+                const int q = qc * 16 * QL + ql + 16 * i;
+                if (q < npairs) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 2 * (4 * blk + j) + par;
+                        if (k < p.n_mfcc) {
+                            P2 cv = acc[i][j];
+                            if (k == 0) {
+                                const P2 cm = fmeanP[q];
+                                cv = pfma(mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr)), bc(p.dct_row0_sum), cv);
+                            }
+                            ctile[k * TC + 2 * q] = cv.lo;
+                            if (2 * q + 1 < p.T) ctile[k * TC + 2 * q + 1] = cv.hi;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------
@@ -275,9 +326,7 @@ __device__ __forceinline__ void load_dtab(const KParams& p, float4* dtab, int wa
 // --------------------------------------------------------------------------------
 // NG / CODE: compile-time shape of the mel ELL bank (NG 16-filter groups, 2 bits per group = float4 steps - 1)
 // for the known presets, so the projection unrolls into straight-line code; NG = 0 -> runtime metadata.
-// NT8: compile-time number of 8-coefficient N-tiles of the tensor-core DCT (0 = runtime p.nt8): a constant
-// trip count keeps the mma.sync sequence free of predicates / WARPSYNCs.
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, int NT8, typename SAMP>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
     constexpr bool PF = false;                              // register prefetch of the next pair: spills at 128 regs, no gain at 168
@@ -304,9 +353,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const float4* f_w4 = reinterpret_cast<const float4*>(smem + p.off_fw4);
     C2* scratch_all = reinterpret_cast<C2*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
-    float* fmean = tile + (p.T + 1) * p.tile_stride;        // MFCC only: [T] frame means, after the dB tile (+1 dummy row)
-    if (FAM == FAM_MFCC && p.use_mma && p.dtab_resident)
-        load_dtab(p, reinterpret_cast<float4*>(smem + p.sm_dtab), tid >> 5, nthr >> 5, tid & 31);
+    // MFCC only: the per-clip dB tile holds one row per frame PAIR, each element an (A, B) pair -- exactly what the
+    // mel stage produces and what the packed DCT consumes; row stride p.tile_stride (P2 units, odd); +1 dummy row
+    P2* tileP = reinterpret_cast<P2*>(tile);
+    P2* fmeanP = tileP + (((p.T + 1) >> 1) + 1) * p.tile_stride;      // per-pair frame means, right after the tile
+    const float* s_dfold = reinterpret_cast<const float*>(smem + p.off_dfold);
     __syncthreads();
 
     const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
@@ -459,10 +510,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     }
                     if (l == 0) pbuf[G::M / 2] = pmid;
                     __syncwarp();
-                    float* orowA = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * p.n_filt
-                                                      : tile + (cA.ok ? cA.t : p.T) * p.tile_stride;
-                    float* orowB = (FAM == FAM_FBANK) ? p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * p.n_filt
-                                                      : tile + (cB.ok ? cB.t : p.T) * p.tile_stride;
+                    float* orowA = p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * p.n_filt;     // FBANK rows
+                    float* orowB = p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * p.n_filt;
+                    P2* prow = tileP + min(q, npairs) * p.tile_stride;                            // MFCC pair row (dummy: npairs)
                     P2 fsum = bc(0.f);
                     // one filter per lane and group; emit() turns the band sum into dB and stores it
                     auto emit = [&](int m, const P2& acc, bool guard) {
@@ -478,8 +528,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                         } else {
                             const float da = 3.010299956639812f * lg2_ftz(fmaxf(acc.lo, p.amin));   // 10 log10
                             const float db = 3.010299956639812f * lg2_ftz(fmaxf(acc.hi, p.amin));
-                            orowA[m] = da;                      // invalid frames go to the dummy row T
-                            orowB[m] = db;
+                            prow[m] = mkp(da, db);              // one STS.64 per filter and frame pair
                             run_max = fmaxf(run_max, fmaxf(cA.ok ? da : -CUDART_INF_F, cB.ok ? db : -CUDART_INF_F));
                             fsum = padd(fsum, mkp(da, db));
                         }
@@ -529,10 +578,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             fsum.lo += __shfl_xor_sync(0xffffffffu, fsum.lo, o);
                             fsum.hi += __shfl_xor_sync(0xffffffffu, fsum.hi, o);
                         }
-                        if (l == 0) {
-                            if (cA.ok) fmean[cA.t] = fsum.lo / (float)p.n_filt;
-                            if (cB.ok) fmean[cB.t] = fsum.hi / (float)p.n_filt;
-                        }
+                        if (l == 0) fmeanP[min(q, npairs)] = pmul(fsum, bc(1.f / (float)p.n_filt));
                     }
                     __syncwarp();
                 }
@@ -567,7 +613,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             }
         }
 
-        if (FAM == FAM_MFCC) {
+        if (FAM == FAM_MFCC && !(p.debug & 1)) {
             __shared__ float s_red[kMaxThreads / 32];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
@@ -579,120 +625,54 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
             // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
             //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
-            // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3: keeps the fp32 /
-            // tensor-core accumulation error an order of magnitude below the 1e-3 tolerance.
-            // coefficient tile [row][TC]: FT output = the tile itself (TC = T, flat vector copy); TF output reads
-            // it transposed, so an odd stride keeps those reads conflict-free
+            // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3.
+            //
+            // The contraction runs on the FP32 pipe in packed FFMA2 (both frames of a pair at once), NOT on tensor
+            // cores: measured on B200, the legacy mma.sync TF32 path retires ~1 HMMA.1688 per 21 cycles per SMSP, i.e.
+            // ~65 fp32-grade MAC/clk/SM after the 3xTF32 split fp32 accuracy needs, against 128 MAC/clk/SM for FFMA2
+            // (profiles/r1_notes.md), and tcgen05 would need split operand tiles that do not fit beside the dB tile.
+            // The DCT-II symmetry D[k][n-1-f] = (-1)^k D[k][f] halves the MACs: even k see s = x[f] + x[n-1-f],
+            // odd k see d = x[f] - x[n-1-f], f < n/2.
             const int TC = (p.layout == SRFE_LAYOUT_FT) ? p.T : p.T + 1 + (p.T & 1);
             const int warp = tid >> 5, nwarps = nthr >> 5;
             float* ctile = reinterpret_cast<float*>(smem + p.sm_ctile);
-            if (p.use_mma) {
-                // ---- tensor-core DCT: C[t][k] = sum_f X[t][f] D[k][f], M = frames, N = coefficients, K = mels.
-                // D lives in shared memory pre-split into TF32 (hi, lo) pairs: resident for the CTA's lifetime
-                // when it fits, otherwise rebuilt per clip on top of the idle FFT scratch.
-                const float4* dtab = reinterpret_cast<const float4*>(smem + p.sm_dtab);
-                const int RS4 = (p.n_filt >> 3) * 4 + 4;
-                if (!p.dtab_resident) load_dtab(p, reinterpret_cast<float4*>(smem + p.sm_dtab), warp, nwarps, lane);
-                if (p.dct_ksplit > 1)
-                    for (int idx = tid; idx < p.n_mfcc * TC; idx += nthr) ctile[idx] = 0.f;
-                __syncthreads();
-                const int g = lane >> 2, qq = lane & 3;
-                const int mtiles = (p.T + 15) >> 4;
-                const int kper = (p.n_filt >> 3) / p.dct_ksplit;
-                constexpr int NTC = NT8 > 0 ? NT8 : 8;      // unrolled N-tile count
-                const int ntn = NT8 > 0 ? NT8 : p.nt8;      // live N-tiles (== NTC when specialised)
-                const float4* dbase = dtab + g * RS4 + qq;
-                for (int task = warp; task < mtiles * p.dct_ksplit; task += nwarps) {
-                    const int mt = task / p.dct_ksplit, kpart = task - mt * p.dct_ksplit;
-                    float acc[NTC][4];
-#pragma unroll
-                    for (int nt = 0; nt < NTC; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-                    const int t0 = mt * 16;
-                    const int tra = min(t0 + g, p.T - 1), trb = min(t0 + g + 8, p.T - 1);
-                    const float* ra = tile + tra * p.tile_stride + qq;
-                    const float* rb = tile + trb * p.tile_stride + qq;
-                    const float ca = fmaxf(fmean[tra], thr), cb = fmaxf(fmean[trb], thr);
-                    for (int ks = kpart * kper; ks < (kpart + 1) * kper; ++ks) {
-                        uint32_t ah[4], al[4];
-                        split_tf32(fmaxf(ra[8 * ks], thr) - ca, ah[0], al[0]);
-                        split_tf32(fmaxf(rb[8 * ks], thr) - cb, ah[1], al[1]);
-                        split_tf32(fmaxf(ra[8 * ks + 4], thr) - ca, ah[2], al[2]);
-                        split_tf32(fmaxf(rb[8 * ks + 4], thr) - cb, ah[3], al[3]);
-                        // the three 3xTF32 products are issued product-major so that consecutive HMMAs hit
-                        // different accumulators (no back-to-back dependency on one tile)
-                        const float4* dk = dbase + 4 * ks;
-                        float4 bf[NTC];
-                        if (NT8 > 0) {
-#pragma unroll
-                            for (int nt = 0; nt < NTC; ++nt) bf[nt] = dk[nt * 8 * RS4];
-#pragma unroll
-                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
-#pragma unroll
-                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
-#pragma unroll
-                            for (int nt = 0; nt < NTC; ++nt) mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
-                        } else {
-#pragma unroll
-                            for (int nt = 0; nt < NTC; ++nt) {
-                                if (nt < ntn) {             // warp-uniform
-                                    bf[nt] = dk[nt * 8 * RS4];
-                                    mma_tf32(acc[nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
-                                    mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].z), __float_as_uint(bf[nt].w));
-                                    mma_tf32(acc[nt], ah, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < NTC; ++nt) {
-                        if (nt < ntn) {
-                            const int k = nt * 8 + 2 * qq, ta = t0 + g, tb = t0 + g + 8;
-                            if (k == 0 && kpart == 0) { acc[nt][0] = fmaf(ca, p.dct_row0_sum, acc[nt][0]); acc[nt][2] = fmaf(cb, p.dct_row0_sum, acc[nt][2]); }
-                            float* c0p = ctile + k * TC;
-                            if (p.dct_ksplit > 1) {
-                                if (k < p.n_mfcc) {
-                                    if (ta < p.T) atomicAdd(c0p + ta, acc[nt][0]);
-                                    if (tb < p.T) atomicAdd(c0p + tb, acc[nt][2]);
-                                }
-                                if (k + 1 < p.n_mfcc) {
-                                    if (ta < p.T) atomicAdd(c0p + TC + ta, acc[nt][1]);
-                                    if (tb < p.T) atomicAdd(c0p + TC + tb, acc[nt][3]);
-                                }
-                            } else {
-                                if (k < p.n_mfcc) {
-                                    if (ta < p.T) c0p[ta] = acc[nt][0];
-                                    if (tb < p.T) c0p[tb] = acc[nt][2];
-                                }
-                                if (k + 1 < p.n_mfcc) {
-                                    if (ta < p.T) c0p[TC + ta] = acc[nt][1];
-                                    if (tb < p.T) c0p[TC + tb] = acc[nt][3];
-                                }
-                            }
-                        }
-                    }
+            const int TSP = p.tile_stride;
+            if (p.dct_fold) {
+                const int half = p.n_filt >> 1;
+                // (1) clamp, re-centre, fold -- in place: s -> [f], d -> [n-1-f]
+                for (int idx = tid; idx < ((p.debug & 16) ? 0 : npairs * half); idx += nthr) {
+                    const int q = idx / half, f = idx - q * half;
+                    P2* row = tileP + q * TSP;
+                    const P2 cm = fmeanP[q];
+                    const P2 c = mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr));
+                    const P2 x0 = row[f], x1 = row[p.n_filt - 1 - f];
+                    const P2 y0 = psub(mkp(fmaxf(x0.lo, thr), fmaxf(x0.hi, thr)), c);
+                    const P2 y1 = psub(mkp(fmaxf(x1.lo, thr), fmaxf(x1.hi, thr)), c);
+                    row[f] = padd(y0, y1);
+                    row[p.n_filt - 1 - f] = psub(y0, y1);
                 }
+                __syncthreads();
+                // (2) the contraction (dct_fold_tasks)
+                const float* dfold = p.dfold_global ? p.dfold_g : s_dfold;
+                if (p.debug & 2) {}
+                else if (npairs <= 32) dct_fold_tasks<2>(p, tileP, dfold, fmeanP, ctile, thr, npairs, TC, warp, nwarps, lane);
+                else                   dct_fold_tasks<4>(p, tileP, dfold, fmeanP, ctile, thr, npairs, TC, warp, nwarps, lane);
             } else {
-                const int kq_n = p.n_mfcc_pad / 4;
-                for (int kq = warp; kq < kq_n; kq += nwarps) {
-                    const float4* dcol = reinterpret_cast<const float4*>(p.dct_t) + kq;
-                    for (int t = lane; t < p.T; t += 32) {
-                        const float* row = tile + t * p.tile_stride;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float ct = fmaxf(fmean[t], thr);
-#pragma unroll 4
-                        for (int f = 0; f < p.n_filt; ++f) {
-                            const float d = fmaxf(row[f], thr) - ct;
-                            const float4 w = __ldg(dcol + f * kq_n);
-                            acc.x = fmaf(w.x, d, acc.x); acc.y = fmaf(w.y, d, acc.y);
-                            acc.z = fmaf(w.z, d, acc.z); acc.w = fmaf(w.w, d, acc.w);
-                        }
-                        const int k0 = 4 * kq;
-                        if (k0 == 0) acc.x = fmaf(ct, p.dct_row0_sum, acc.x);
-                        ctile[(k0 + 0) * TC + t] = acc.x;
-                        if (k0 + 1 < p.n_mfcc) ctile[(k0 + 1) * TC + t] = acc.y;
-                        if (k0 + 2 < p.n_mfcc) ctile[(k0 + 2) * TC + t] = acc.z;
-                        if (k0 + 3 < p.n_mfcc) ctile[(k0 + 3) * TC + t] = acc.w;
+                // generic path (odd n_mels): plain packed dot products against the global DCT rows
+                for (int task = tid; task < p.n_mfcc * npairs; task += nthr) {
+                    const int k = task / npairs, q = task - k * npairs;
+                    const P2* row = tileP + q * TSP;
+                    const P2 cm = fmeanP[q];
+                    const P2 c = mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr));
+                    const float* dk = p.dct_kf + k * p.n_filt;
+                    P2 acc = bc(0.f);
+                    for (int f = 0; f < p.n_filt; ++f) {
+                        const P2 x = row[f];
+                        acc = pfma(psub(mkp(fmaxf(x.lo, thr), fmaxf(x.hi, thr)), c), bc(__ldg(dk + f)), acc);
                     }
+                    if (k == 0) acc = pfma(c, bc(p.dct_row0_sum), acc);
+                    ctile[k * TC + 2 * q] = acc.lo;
+                    if (2 * q + 1 < p.T) ctile[k * TC + 2 * q + 1] = acc.hi;
                 }
             }
             __syncthreads();
@@ -715,7 +695,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const int R = (1 + p.n_deltas) * p.n_mfcc;
             float* oc = p.out + (long long)clip0 * R * p.T;
             if (p.layout == SRFE_LAYOUT_FT) {
-                const int n = R * p.T;                       // the clip's features are one contiguous block
+                const int n = (p.debug & 8) ? 0 : R * p.T;   // the clip's features are one contiguous block
                 if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(oc) & 15) == 0)) {
                     const float4* c4 = reinterpret_cast<const float4*>(ctile);
                     float4* o4 = reinterpret_cast<float4*>(oc);
