@@ -326,10 +326,12 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 // Fitted to scripts/tune.py sweeps on the B200: throughput ~ round efficiency x (resident warps - 2.3)^0.8;
                 // for MFCC (CTA barriers + serial epilogue) two co-resident CTAs are worth ~1.6x one CTA at equal warps,
                 // for SPEC / FBANK (no barriers) the CTA count does not matter.
+                // The FT spectrogram tile (one CTA barrier per round) wants exactly filled rounds and few clips per group.
+                const bool ft = e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT;
                 double score = (double)nf / (double)(rounds * per_round);
-                score *= std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
+                score *= std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), ft ? 0.5 : 0.8);
                 if (ctas == 2) score *= (e->family == FAM_MFCC) ? 1.6 : 1.02;
-                score *= 1.0 - 0.004 * (cpc - 1);
+                score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 - 0.004 * (cpc - 1);
                 if (score > best + 1e-9) { best = score; bc = pl; bc.warps = warps; bc.ctas = ctas; bc.cpc = cpc; }
             }
         }
