@@ -268,7 +268,7 @@ __device__ __forceinline__ void dct_fold_tasks(const KParams& p, const P2* tileP
 #pragma unroll
         for (int i = 0; i < QL; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = bc(0.f); }
         if (par == 0) {
-#pragma unroll 2
+#pragma unroll 4
             for (int f = 0; f < f1 - f0; ++f) {
                 const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
 #pragma unroll
@@ -279,7 +279,7 @@ __device__ __forceinline__ void dct_fold_tasks(const KParams& p, const P2* tileP
                 }
             }
         } else {
-#pragma unroll 2
+#pragma unroll 4
             for (int f = 0; f < f1 - f0; ++f) {
                 const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
 #pragma unroll

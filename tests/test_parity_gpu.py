@@ -374,3 +374,44 @@ def test_results_do_not_depend_on_launch_configuration(srfe_lib, corpus, monkeyp
                 torch.testing.assert_close(y1, base, rtol=0, atol=2e-4)
             else:
                 assert torch.equal(y1, base), f"configuration-dependent result: {type(p).__name__} cfg={cfg}"
+
+
+def test_thread_safety_two_host_threads(srfe_lib, corpus):
+    """Re-entrancy (SURVEY 8b 'Threading'): two host threads, each on its own stream, hammer different feature
+    families (first calls race on the table cache); results must equal the single-threaded ones."""
+    import threading
+    x = torch.from_numpy(corpus).cuda()
+    p1 = S.MfccParams(n_fft=512, win_length=400, hop=160, n_mels=64, n_mfcc=20, n_deltas=1)     # fresh cache entries
+    p2 = S.FbankParams(nfilt=48)
+    want = {}
+    errs = []
+
+    def work(name, fn, p):
+        try:
+            st = torch.cuda.Stream()
+            outs = []
+            with torch.cuda.stream(st):
+                for _ in range(20):
+                    outs.append(fn(x, p))
+            st.synchronize()
+            assert all(torch.equal(o, outs[0]) for o in outs)
+            want[name] = outs[0]
+        except Exception as e:          # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=("a", S.mfcc, p1)), threading.Thread(target=work, args=("b", S.fbank, p2)),
+          threading.Thread(target=work, args=("c", S.mfcc, p1))]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert not errs, errs
+    assert torch.equal(want["a"], want["c"]) and torch.equal(want["a"], S.mfcc(x, p1)) and torch.equal(want["b"], S.fbank(x, p2))
+    # host entry points from two threads (per-thread staging workspaces)
+    xc = torch.from_numpy(corpus)
+    res = {}
+    def host(name):
+        res[name] = S.mfcc(xc, S.R_MFCC)
+    hs = [threading.Thread(target=host, args=(i,)) for i in range(3)]
+    for t in hs: t.start()
+    for t in hs: t.join()
+    ref = S.mfcc(x, S.R_MFCC).cpu()
+    assert all(torch.equal(res[i], ref) for i in range(3))
