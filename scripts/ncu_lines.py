@@ -50,3 +50,16 @@ def text(loc):
 print(f"{kname}\ninstr {tot_i:.0f} samples {tot_s:.0f}")
 for loc, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
     print(f"{100*i/tot_i:5.1f}%i {100*s/max(tot_s,1):5.1f}%s  {loc[0]}:{loc[1]:<4d} {text(loc)}")
+if os.environ.get("REGIONS"):
+    # address-ordered view: each SASS instruction is charged to the most recent srfe_kernels.cuh line (inlined helpers
+    # inherit their caller); consecutive instructions in the same 10-line bucket are merged
+    print("\naddress-ordered regions (sticky srfe_kernels.cuh line, merged per 10-line bucket; >= 0.3 % of samples)")
+    sticky, runs = 0, []
+    for r, loc in zip(body, lines):
+        if loc[0] == "srfe_kernels.cuh": sticky = loc[1]
+        b = sticky // 10
+        i = float(r[ci["Instructions Executed"]] or 0); s = float(r[ci["# Samples"]] or 0)
+        if runs and runs[-1][0] == b: runs[-1][1] += i; runs[-1][2] += s; runs[-1][3] += 1
+        else: runs.append([b, i, s, 1])
+    for b, i, s, n in runs:
+        if s / tot_s >= 0.003: print(f"  lines {10*b:4d}-{10*b+9:<4d} sass {n:5d}  {100*i/tot_i:5.1f}%i {100*s/tot_s:5.1f}%s")

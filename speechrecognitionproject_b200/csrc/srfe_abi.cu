@@ -40,8 +40,9 @@ struct Entry {
     int blob_smem = 0;
     void* d_blob = nullptr;
     void* d_dct_kf = nullptr;
-    void* d_dfold = nullptr;
-    int dfold_bytes = 0;
+    struct DctVar { int cb, nbe, nbo, off, bytes; };
+    std::vector<DctVar> dct_vars;   // folded DCT table, one copy per coefficient-block size (tail of the device blob)
+    int blob_common = 0;        // bytes every CTA copies to shared memory; one DCT variant follows it there
     int mel_ng = 0;             // ELL shape: groups and 2-bit run-length code (0 groups = not encodable)
     unsigned mel_code = 0;
     int n_bins = 0;
@@ -210,23 +211,28 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     double rs0 = 0.0;
     for (int f = 0; f < p.n_mels; ++f) rs0 += dct[f];
     e->kp.dct_row0_sum = (float)rs0;                                   // = sqrt(n_mels)
-    // folded DCT table (even n_mels): [parity][f < n/2][NJ], coefficient k = 2 j + parity, NJ padded to 4s
-    e->kp.dct_fold = (p.n_mels % 2 == 0 && p.n_mels >= 4 && (p.n_mels / 2) % 2 == 0) ? 1 : 0;
+    // Folded DCT tables (n_mels % 4 == 0).  The DCT-II symmetry D[k][n-1-f] = (-1)^k D[k][f] lets even k work on
+    // s[f] = x[f] + x[n-1-f] and odd k on d[f] = x[f] - x[n-1-f], f < n/2.  One kernel thread owns one frame pair and
+    // one block of CB same-parity coefficients; the table of a block is [f < n/2][RW] floats (RW = 4 or 8, zero
+    // padded) so a thread reads its coefficients for one f with one or two LDS.128.  Which CB fills the CTA best
+    // depends on the frame count and the launch shape, so every CB gets its own copy after the common tables.
+    e->kp.dct_fold = (p.n_mels >= 4 && p.n_mels % 4 == 0) ? 1 : 0;
+    e->blob_common = (int)bb.data.size();
     if (e->kp.dct_fold) {
-        // [parity][f < n/2][NJ] floats, coefficient k = 2 j + parity at column j, NJ padded to a multiple of 4
-        const int half = p.n_mels / 2, ne = (p.n_mfcc + 1) / 2;
-        const int NJ = ((ne + 3) / 4) * 4;
-        std::vector<float> fold((size_t)2 * half * NJ, 0.f);
-        for (int k = 0; k < p.n_mfcc; ++k)
-            for (int f = 0; f < half; ++f)
-                fold[((size_t)(k & 1) * half + f) * NJ + (k >> 1)] = (float)dct[(size_t)k * p.n_mels + f];
-        e->kp.dct_nj = NJ;
-        e->dfold_bytes = (int)fold.size() * 4;
-        e->kp.off_dfold = bb.add(fold.data(), fold.size() * 4);      // last blob item: can be left out of the smem copy
-        if (cudaMalloc(&e->d_dfold, fold.size() * 4) != cudaSuccess ||
-            cudaMemcpy(e->d_dfold, fold.data(), fold.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
-            return cuda_fail(cudaGetLastError(), "dfold upload");
-        e->kp.dfold_g = (const float*)e->d_dfold;
+        const int half = p.n_mels / 2, ne = (p.n_mfcc + 1) / 2, no = p.n_mfcc / 2;
+        for (int cb : {2, 3, 4, 5, 6, 8}) {
+            const int rw = cb <= 4 ? 4 : 8;
+            Entry::DctVar v{cb, (ne + cb - 1) / cb, (no + cb - 1) / cb, 0, 0};
+            std::vector<float> tab((size_t)(v.nbe + v.nbo) * half * rw, 0.f);
+            for (int k = 0; k < p.n_mfcc; ++k) {
+                const int j = k >> 1, blk = (k & 1) * v.nbe + j / cb;
+                for (int f = 0; f < half; ++f)
+                    tab[((size_t)blk * half + f) * rw + j % cb] = (float)dct[(size_t)k * p.n_mels + f];
+            }
+            v.bytes = (int)tab.size() * 4;
+            v.off = bb.add(tab.data(), tab.size() * 4);
+            e->dct_vars.push_back(v);
+        }
     }
     std::vector<float> dct_kf((size_t)p.n_mfcc * p.n_mels);
     for (size_t i = 0; i < dct_kf.size(); ++i) dct_kf[i] = (float)dct[i];
@@ -272,7 +278,7 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
     return SRFE_OK;
 }
 
-struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, dfold_global, blob; };
+struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var; };
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -284,9 +290,21 @@ static int env_int(const char* name, int dflt) {
 static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, Config* c) {
     (void)budget;
     const int hw = 2 * warps;
-    const bool dg = e->family == FAM_MFCC && e->dfold_bytes > 0 && env_int("SRFE_DFOLD_GLOBAL", 0);
-    const int blob = align16(e->blob_smem - (dg ? e->dfold_bytes : 0));   // the folded DCT table is the blob's tail
-    c->dfold_global = dg ? 1 : 0;
+    int blob = align16(e->blob_smem);
+    c->dct_var = -1;
+    if (!e->dct_vars.empty()) {
+        // DCT block size: fewest passes of the CTA's threads over the (coefficient block, frame pair) items, then
+        // the cheaper thread (2 cycles per FFMA2 + ~6 for loads and loop)
+        const long long npairs = (kp.T + 1) / 2, nthr = 32LL * warps;
+        long long best = -1;
+        for (size_t i = 0; i < e->dct_vars.size(); ++i) {
+            const Entry::DctVar& v = e->dct_vars[i];
+            const long long items = (long long)(v.nbe + v.nbo) * npairs;
+            const long long cost = ((items + nthr - 1) / nthr) * (2 * v.cb + 6);
+            if (best < 0 || cost < best) { best = cost; c->dct_var = (int)i; }
+        }
+        blob = align16(e->blob_common + e->dct_vars[c->dct_var].bytes);
+    }
     c->blob = blob;
     int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 16;
     int tile = 0;
@@ -309,7 +327,7 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
 // warps resident as the shared-memory budget allows, prefer two CTAs per SM (their phases overlap).
 static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Config* out) {
     double best = -1.0;
-    Config bc{0, 0, 1, 0, 0, 0, 0, 0, 0};
+    Config bc{0, 0, 1, 0, 0, 0, 0, 0, -1};
     int cpc_max = (e->family == FAM_MFCC) ? 1 : 8;
     if (8.0 * kp.T * kp.T >= 4294967296.0) cpc_max = 1;              // magic division range (frame_pos)
     const int per_sm = 228 * 1024;                                   // B200: 228 KB per SM, 1 KB reserved per CTA
@@ -365,8 +383,13 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     kp.n_groups = (kp.n_clips + cfg.cpc - 1) / cfg.cpc;
     kp.sm_scratch = cfg.blob;
     kp.sm_tile = kp.sm_scratch + cfg.scratch;
-    kp.dfold_global = cfg.dfold_global;
-    kp.blob_bytes = cfg.blob;                                        // smem copy stops before the table when it stays global
+    kp.blob_bytes = cfg.blob;
+    if (cfg.dct_var >= 0) {
+        const Entry::DctVar& v = e->dct_vars[cfg.dct_var];
+        kp.blob_bytes = e->blob_common;
+        kp.dct_cb = v.cb; kp.dct_nbe = v.nbe; kp.dct_nbo = v.nbo;
+        kp.dct_src = v.off; kp.dct_bytes = v.bytes; kp.off_dfold = e->blob_common;
+    }
     kp.sm_ctile = cfg.ctile_off;
     kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
     kp.sw_prefetch = env_int("SRFE_SWPF", 0);                        // measured: no effect (loads are not the limiter)

@@ -50,7 +50,7 @@ struct KParams {
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
     int blob_bytes;                    // multiple of 16
     int off_win, off_tw1, off_twu, off_tw16;
-    int off_gm, off_fs, off_fw4;       // mel ELL: int2 {w4 offset, n4} per 16-filter group; start bin per filter; float4 weights
+    int off_gm, off_fs, off_fw4;       // mel ELL: int2 {w4 offset, n4} per 16-filter group; start bin per filter; planar float2 weights
     int n_filt, n_fgroups;
     float scale, log_eps;
     int take_log, layout;
@@ -58,8 +58,9 @@ struct KParams {
     int n_mfcc, n_mfcc_pad, n_deltas;
     float top_db, amin, dct_row0_sum;
     const float* dct_kf;               // global [n_mfcc][n_mels] DCT-II rows (generic path, odd n_mels)
-    const float* dfold_g; int dfold_global;   // the same table in global memory
-    int dct_fold, dct_nj, off_dfold;   // folded DCT table in the blob: [parity][f < n/2][dct_nj] floats (dct_nj % 4 == 0)
+    int dct_fold, off_dfold;           // folded DCT table: shared-memory offset (right after the common tables)
+    int dct_cb, dct_nbe, dct_nbo;      //   coefficients per block, even / odd block counts
+    int dct_src, dct_bytes;            //   where the chosen block-size variant sits in the global blob
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
     int w_lo, w_hi;                    // non-zero extent of the window (informational)
@@ -240,82 +241,52 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 
 // --------------------------------------------------------------------------------
 // folded DCT-II on the FP32 pipe (see the epilogue comment in the kernel)
-//   warp task = (parity, block of 4 coefficients, chunk of 16 QL frame pairs): lane (fh, ql) takes the pairs
-//   ql, ql + 16, ... and half of the f range; per f one LDS.128 brings the 4 coefficients (broadcast) and QL LDS.64
-//   the pairs -> 4 QL FFMA2.  The two f halves are combined with one shuffle: no atomics, deterministic.
-//   Table layout: [parity][f < n/2][NJ] floats, NJ = coefficients per parity padded to a multiple of 4.
-//   (Measured alternatives, both slower: 5-coefficient blocks split over warps with shared-memory atomics; the table
-//   read through L1 from global memory to make room for a second CTA per SM.)
+//   work item = (block of CB same-parity coefficients, frame pair); one THREAD per item, items dealt over the whole
+//   CTA, so every warp is busy and nothing is combined across lanes.  Per f the thread reads its pair's folded value
+//   (LDS.64) and its block's CB coefficients (one or two LDS.128, the same address for all lanes of a block) and
+//   issues CB FFMA2.  Table layout: [block][f < n/2][RW] floats, RW = 4 (CB <= 4) or 8, even-k blocks first.
+//   The host picks CB so that the items fill one pass of the CTA (srfe_abi.cu: smem_plan).
+//   Measured alternatives, all slower: warp tasks of 4 coefficients x 64 pairs with the f range split over half-warps
+//   (10 tasks for 13-14 warps, ~550 instructions of per-task set-up / shuffle combine / stores against 512 FFMA2);
+//   5-coefficient blocks with shared-memory atomics; the table read through L1 from global memory.
 // --------------------------------------------------------------------------------
-template <int QL>
-__device__ __forceinline__ void dct_fold_tasks(const KParams& p, const P2* tileP, const float* dfold, const P2* fmeanP,
-                                               float* ctile, float thr, int npairs, int TC, int warp, int nwarps, int lane) {
-    const int half = p.n_filt >> 1, NJ = p.dct_nj, TSP = p.tile_stride;
-    const int nblk = NJ >> 2, qchunks = (npairs + 16 * QL - 1) / (16 * QL);
-    const int fh = lane >> 4, ql = lane & 15, fspan = half >> 1;
-    for (int task = warp; task < 2 * nblk * qchunks; task += nwarps) {
-        const int qc = task % qchunks, kb = task / qchunks;
-        const int par = kb / nblk, blk = kb - par * nblk;
-        const int f0 = fh * fspan, f1 = (fh == 0) ? fspan : half;
-        const P2* xr[QL];
+template <int CB>
+__device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, const float* dtab, const P2* fmeanP,
+                                          float* ctile, float thr, int npairs, int TC, int tid, int nthr) {
+    constexpr int RW = CB <= 4 ? 4 : 8;
+    const int half = p.n_filt >> 1, TSP = p.tile_stride;
+    const int nitems = (p.dct_nbe + p.dct_nbo) * npairs;
+    for (int it = tid; it < nitems; it += nthr) {
+        const int b = it / npairs, q = it - b * npairs;
+        const int par = b >= p.dct_nbe ? 1 : 0;
+        const P2* x = tileP + q * TSP + par * half;                    // s[0..half) then d[0..half), both ascending
+        const float4* d = reinterpret_cast<const float4*>(dtab) + b * half * (RW / 4);
+        P2 acc[CB];
 #pragma unroll
-        for (int i = 0; i < QL; ++i) {
-            const int q = min(qc * 16 * QL + ql + 16 * i, npairs - 1);
-            xr[i] = tileP + q * TSP + (par == 0 ? f0 : p.n_filt - 1 - f0);       // even k: s[f] upwards; odd k: d[n-1-f] downwards
-        }
-        const float* dr = dfold + (par * half + f0) * NJ + 4 * blk;
-        P2 acc[QL][4];
-#pragma unroll
-        for (int i = 0; i < QL; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = bc(0.f); }
-        if (par == 0) {
+        for (int j = 0; j < CB; ++j) acc[j] = bc(0.f);
 #pragma unroll 4
-            for (int f = 0; f < f1 - f0; ++f) {
-                const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
+        for (int f = 0; f < half; ++f) {
+            const P2 xv = x[f];
+            float c[8];
+            const float4 d0 = d[f * (RW / 4)];
+            c[0] = d0.x; c[1] = d0.y; c[2] = d0.z; c[3] = d0.w;
+            if (RW == 8) { const float4 d1 = d[f * 2 + 1]; c[4] = d1.x; c[5] = d1.y; c[6] = d1.z; c[7] = d1.w; }
 #pragma unroll
-                for (int i = 0; i < QL; ++i) {
-                    const P2 x = xr[i][f];
-                    acc[i][0] = pfma(x, bc(d.x), acc[i][0]); acc[i][1] = pfma(x, bc(d.y), acc[i][1]);
-                    acc[i][2] = pfma(x, bc(d.z), acc[i][2]); acc[i][3] = pfma(x, bc(d.w), acc[i][3]);
-                }
-            }
-        } else {
-#pragma unroll 4
-            for (int f = 0; f < f1 - f0; ++f) {
-                const float4 d = *reinterpret_cast<const float4*>(dr + f * NJ);
-#pragma unroll
-                for (int i = 0; i < QL; ++i) {
-                    const P2 x = xr[i][-f];
-                    acc[i][0] = pfma(x, bc(d.x), acc[i][0]); acc[i][1] = pfma(x, bc(d.y), acc[i][1]);
-                    acc[i][2] = pfma(x, bc(d.z), acc[i][2]); acc[i][3] = pfma(x, bc(d.w), acc[i][3]);
-                }
-            }
+            for (int j = 0; j < CB; ++j) acc[j] = pfma(xv, bc(c[j]), acc[j]);
         }
+        const int k0 = 2 * CB * (b - par * p.dct_nbe) + par;
+        if (k0 == 0) {                                                  // put the frame's centre back on c0
+            const P2 cm = fmeanP[q];
+            acc[0] = pfma(mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr)), bc(p.dct_row0_sum), acc[0]);
+        }
+        float* cq = ctile + 2 * q;
+        const bool two = 2 * q + 1 < p.T;
 #pragma unroll
-        for (int i = 0; i < QL; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[i][j].lo += __shfl_xor_sync(0xffffffffu, acc[i][j].lo, 16);
-                acc[i][j].hi += __shfl_xor_sync(0xffffffffu, acc[i][j].hi, 16);
-            }
-        if (fh == 0) {
-#pragma unroll
-            for (int i = 0; i < QL; ++i) {
-                const int q = qc * 16 * QL + ql + 16 * i;
-                if (q < npairs) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = 2 * (4 * blk + j) + par;
-                        if (k < p.n_mfcc) {
-                            P2 cv = acc[i][j];
-                            if (k == 0) {
-                                const P2 cm = fmeanP[q];
-                                cv = pfma(mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr)), bc(p.dct_row0_sum), cv);
-                            }
-                            ctile[k * TC + 2 * q] = cv.lo;
-                            if (2 * q + 1 < p.T) ctile[k * TC + 2 * q + 1] = cv.hi;
-                        }
-                    }
-                }
+        for (int j = 0; j < CB; ++j) {
+            const int k = k0 + 2 * j;
+            if (k < p.n_mfcc) {
+                cq[k * TC] = acc[j].lo;
+                if (two) cq[k * TC + 1] = acc[j].hi;
             }
         }
     }
@@ -342,6 +313,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
         const int4* src = reinterpret_cast<const int4*>(p.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < p.blob_bytes / 16; i += nthr) dst[i] = __ldg(src + i);
+        if (FAM == FAM_MFCC && p.dct_fold) {                // the chosen block-size variant of the folded DCT table
+            const int4* vs = reinterpret_cast<const int4*>(p.blob + p.dct_src);
+            int4* vd = reinterpret_cast<int4*>(smem + p.off_dfold);
+            for (int i = tid; i < p.dct_bytes / 16; i += nthr) vd[i] = __ldg(vs + i);
+        }
     }
     const float* s_win = reinterpret_cast<const float*>(smem + p.off_win);
     FftTables T;
@@ -350,7 +326,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     T.tw16 = reinterpret_cast<const cpx*>(smem + p.off_tw16);
     const int2* g_meta = reinterpret_cast<const int2*>(smem + p.off_gm);
     const int* f_start = reinterpret_cast<const int*>(smem + p.off_fs);
-    const float4* f_w4 = reinterpret_cast<const float4*>(smem + p.off_fw4);
+    const float2* f_w2 = reinterpret_cast<const float2*>(smem + p.off_fw4);     // [step][plane][lane]: two LDS.64 per step
     C2* scratch_all = reinterpret_cast<C2*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
     // MFCC only: the per-clip dB tile holds one row per frame PAIR, each element an (A, B) pair -- exactly what the
@@ -540,16 +516,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
                             const int m = 16 * i + l;
                             const P2* pq = pbuf + f_start[m];
-                            const float4* wq = f_w4 + off4 * 16 + l;
+                            const float2* wq = f_w2 + off4 * 32 + l;
                             P2 acc = bc(0.f);
 #pragma unroll
                             for (int q4 = 0; q4 < 4; ++q4) {
                                 if (q4 < n4) {
-                                    const float4 w = wq[q4 * 16];
-                                    acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
-                                    acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
-                                    acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
-                                    acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                                    const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
+                                    acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
+                                    acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
+                                    acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
+                                    acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
                                 }
                             }
                             off4 += n4;
@@ -560,14 +536,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             const int2 gm = g_meta[i];
                             const int m = 16 * i + l;
                             const P2* pq = pbuf + f_start[m];
-                            const float4* wq = f_w4 + gm.x * 16 + l;
+                            const float2* wq = f_w2 + gm.x * 32 + l;
                             P2 acc = bc(0.f);
                             for (int q4 = 0; q4 < gm.y; ++q4) {
-                                const float4 w = wq[q4 * 16];
-                                acc = pfma(pq[4 * q4 + 0], bc(w.x), acc);
-                                acc = pfma(pq[4 * q4 + 1], bc(w.y), acc);
-                                acc = pfma(pq[4 * q4 + 2], bc(w.z), acc);
-                                acc = pfma(pq[4 * q4 + 3], bc(w.w), acc);
+                                const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
+                                acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
+                                acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
+                                acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
+                                acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
                             }
                             emit(m, acc, true);
                         }
@@ -639,24 +615,34 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const int TSP = p.tile_stride;
             if (p.dct_fold) {
                 const int half = p.n_filt >> 1;
-                // (1) clamp, re-centre, fold -- in place: s -> [f], d -> [n-1-f]
-                for (int idx = tid; idx < ((p.debug & 16) ? 0 : npairs * half); idx += nthr) {
-                    const int q = idx / half, f = idx - q * half;
+                // (1) clamp, re-centre, fold -- in place: s[f] -> [f], d[f] -> [n/2 + f].  One item folds f and
+                //     n/2-1-f together: it reads and writes the same four slots, so no other thread's input is touched.
+                const int hq = half >> 1;
+                for (int idx = tid; idx < ((p.debug & 16) ? 0 : npairs * hq); idx += nthr) {
+                    const int q = idx / hq, f = idx - q * hq, g = half - 1 - f;
                     P2* row = tileP + q * TSP;
                     const P2 cm = fmeanP[q];
                     const P2 c = mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr));
-                    const P2 x0 = row[f], x1 = row[p.n_filt - 1 - f];
-                    const P2 y0 = psub(mkp(fmaxf(x0.lo, thr), fmaxf(x0.hi, thr)), c);
-                    const P2 y1 = psub(mkp(fmaxf(x1.lo, thr), fmaxf(x1.hi, thr)), c);
-                    row[f] = padd(y0, y1);
-                    row[p.n_filt - 1 - f] = psub(y0, y1);
+                    const P2 a0 = row[f], a1 = row[p.n_filt - 1 - f], b0 = row[g], b1 = row[p.n_filt - 1 - g];
+                    const P2 ya0 = psub(mkp(fmaxf(a0.lo, thr), fmaxf(a0.hi, thr)), c);
+                    const P2 ya1 = psub(mkp(fmaxf(a1.lo, thr), fmaxf(a1.hi, thr)), c);
+                    const P2 yb0 = psub(mkp(fmaxf(b0.lo, thr), fmaxf(b0.hi, thr)), c);
+                    const P2 yb1 = psub(mkp(fmaxf(b1.lo, thr), fmaxf(b1.hi, thr)), c);
+                    row[f] = padd(ya0, ya1);
+                    row[g] = padd(yb0, yb1);
+                    row[half + f] = psub(ya0, ya1);
+                    row[half + g] = psub(yb0, yb1);
                 }
                 __syncthreads();
-                // (2) the contraction (dct_fold_tasks)
-                const float* dfold = p.dfold_global ? p.dfold_g : s_dfold;
-                if (p.debug & 2) {}
-                else if (npairs <= 32) dct_fold_tasks<2>(p, tileP, dfold, fmeanP, ctile, thr, npairs, TC, warp, nwarps, lane);
-                else                   dct_fold_tasks<4>(p, tileP, dfold, fmeanP, ctile, thr, npairs, TC, warp, nwarps, lane);
+                // (2) the contraction
+                if (!(p.debug & 2)) switch (p.dct_cb) {
+                    case 2: dct_items<2>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                    case 3: dct_items<3>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                    case 4: dct_items<4>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                    case 5: dct_items<5>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                    case 6: dct_items<6>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                    default: dct_items<8>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+                }
             } else {
                 // generic path (odd n_mels): plain packed dot products against the global DCT rows
                 for (int task = tid; task < p.n_mfcc * npairs; task += nthr) {

@@ -3,6 +3,7 @@
 // the oracle's numpy tables is asserted by tests/test_tables.py (no GPU needed).
 #include "srfe_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 
@@ -168,6 +169,45 @@ void to_sparse(const std::vector<double>& dense, int n_filters, int n_bins, doub
     }
 }
 
+// Shared-memory bank skew of one 16-filter group.  Lane l reads the packed power values P[start_l + j] (8 bytes each,
+// 16 bank pairs), so two lanes whose starts agree mod 16 serialise.  A filter may start up to `slack_l` bins early
+// (leading zero weights) without lengthening the group's run: pick the shifts that minimise the worst multiplicity
+// of a bank pair.  Capacitated bipartite matching lanes -> residues by augmenting paths, capacity 1, 2, ...
+static void skew_group(const int* start, const int* slack, int* shift) {
+    for (int cap = 1; cap <= 16; ++cap) {
+        int owner[16][16], used[16] = {0}, res_of[16];
+        for (int l = 0; l < 16; ++l) res_of[l] = -1;
+        bool ok = true;
+        for (int l0 = 0; l0 < 16 && ok; ++l0) {
+            // BFS-free augmenting search (16 x 16: plain DFS with a visited mask per attempt)
+            bool seen[16] = {false};
+            struct Rec { static bool go(int l, const int* start, const int* slack, int cap, int owner[16][16], int* used,
+                                        int* res_of, bool* seen) {
+                for (int d = 0; d <= slack[l]; ++d) {
+                    const int r = ((start[l] - d) % 16 + 16) % 16;
+                    if (seen[r]) continue;
+                    seen[r] = true;
+                    if (used[r] < cap) { owner[r][used[r]++] = l; res_of[l] = r; return true; }
+                    for (int i = 0; i < used[r]; ++i) {
+                        const int o = owner[r][i];
+                        if (go(o, start, slack, cap, owner, used, res_of, seen)) { owner[r][i] = l; res_of[l] = r; return true; }
+                    }
+                }
+                return false;
+            } };
+            ok = Rec::go(l0, start, slack, cap, owner, used, res_of, seen);
+        }
+        if (!ok) continue;
+        for (int l = 0; l < 16; ++l) {
+            shift[l] = 0;
+            for (int d = 0; d <= slack[l]; ++d)
+                if (((start[l] - d) % 16 + 16) % 16 == res_of[l]) { shift[l] = d; break; }
+        }
+        return;
+    }
+    for (int l = 0; l < 16; ++l) shift[l] = 0;
+}
+
 void to_ell(const SparseBank& sb, EllBank& out) {
     const int n = (int)sb.start.size();
     out.groups = (n + 15) / 16;
@@ -183,13 +223,26 @@ void to_ell(const SparseBank& sb, EllBank& out) {
         out.gmeta[2 * g] = off4;
         out.gmeta[2 * g + 1] = n4;
         out.w4.resize((size_t)(off4 + n4) * 16 * 4, 0.f);
+        int st[16], slack[16], shift[16];
         for (int l = 0; l < 16; ++l) {
             const int m = 16 * g + l;
+            const bool live = m < n && sb.count[m] > 0;
+            // empty / padding lanes read (and ignore) 4 * n4 values from anywhere: any residue will do
+            st[l] = live ? sb.start[m] : 15;
+            slack[l] = live ? std::min(4 * n4 - sb.count[m], sb.start[m]) : 15;
+        }
+        skew_group(st, slack, shift);
+        for (int l = 0; l < 16; ++l) {
+            const int m = 16 * g + l;
+            const int s0 = st[l] - shift[l];
+            out.start[m] = s0;
             if (m >= n) continue;
-            out.start[m] = sb.start[m];
-            for (int q = 0; q < sb.count[m]; ++q)
-                out.w4[((size_t)(off4 + q / 4) * 16 + l) * 4 + (q & 3)] = sb.weight[sb.offset[m] + q];
-            if (sb.start[m] + 4 * n4 > out.max_reach) out.max_reach = sb.start[m] + 4 * n4;
+            for (int q = 0; q < sb.count[m]; ++q) {
+                const int qq = q + shift[l];
+                // planar: [(run step)][plane = (qq & 3) / 2][lane] float2 -> two conflict-free LDS.64 per step
+                out.w4[(((size_t)(off4 + qq / 4) * 2 + ((qq & 3) >> 1)) * 16 + l) * 2 + (qq & 1)] = sb.weight[sb.offset[m] + q];
+            }
+            if (s0 + 4 * n4 > out.max_reach) out.max_reach = s0 + 4 * n4;
         }
         off4 += n4;
     }

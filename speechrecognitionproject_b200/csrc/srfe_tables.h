@@ -45,8 +45,8 @@ void to_sparse(const std::vector<double>& dense, int n_filters, int n_bins, doub
 //     multiple-of-4 run length so the inner loop has a uniform trip count and reads float4 weights
 struct EllBank {
     std::vector<int32_t> gmeta;      // per group: {offset into w4 (float4 units, /16 lanes), n4 = run length / 4}
-    std::vector<int32_t> start;      // per filter (padded to 16 * groups): first bin
-    std::vector<float> w4;           // [(offset + q4) * 16 + lane] float4 = 4 consecutive weights
+    std::vector<int32_t> start;      // per filter (padded to 16 * groups): first bin read (bank-skewed, <= first nonzero bin)
+    std::vector<float> w4;           // [((offset + q4) * 2 + plane) * 16 + lane] float2: weights 2 plane, 2 plane + 1 of step q4
     int groups = 0;
     int max_reach = 0;               // max over filters of start + 4 * n4 (bins read, incl. padding)
 };
