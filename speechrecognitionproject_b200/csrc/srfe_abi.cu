@@ -278,7 +278,7 @@ static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cu
     return SRFE_OK;
 }
 
-struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var; };
+struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var, dct_pq; };
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -292,17 +292,29 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
     const int hw = 2 * warps;
     int blob = align16(e->blob_smem);
     c->dct_var = -1;
+    c->dct_pq = 1;
     if (!e->dct_vars.empty()) {
-        // DCT block size: fewest passes of the CTA's threads over the (coefficient block, frame pair) items, then
-        // the cheaper thread (2 cycles per FFMA2 + ~6 for loads and loop)
+        // DCT tile (CB coefficients x PQ frame pairs per thread): modelled cycles per clip = passes over the CTA's
+        // threads x max(shared-memory wavefronts of all busy warps, FFMA2 issue on the busiest sub-partition), per f:
+        //   LDS.64 of a pair 2 cycles, coefficient LDS.128 (one address) 2 cycles (+ ~1 for a 5th/6th), FFMA2 2 cycles
+        //   (scripts/ubench/lds_issue.cu)
         const long long npairs = (kp.T + 1) / 2, nthr = 32LL * warps;
-        long long best = -1;
+        double best = -1.0;
         for (size_t i = 0; i < e->dct_vars.size(); ++i) {
             const Entry::DctVar& v = e->dct_vars[i];
-            const long long items = (long long)(v.nbe + v.nbo) * npairs;
-            const long long cost = ((items + nthr - 1) / nthr) * (2 * v.cb + 6);
-            if (best < 0 || cost < best) { best = cost; c->dct_var = (int)i; }
+            for (int pq = 1; pq <= 2; ++pq) {
+                const long long items = (long long)(v.nbe + v.nbo) * ((npairs + pq - 1) / pq);
+                const long long passes = (items + nthr - 1) / nthr;
+                const double busy = std::min((double)items / passes, (double)nthr) / 32.0;      // warps per pass
+                const double smem = busy * (2.0 * pq + (v.cb <= 4 ? 2.0 : v.cb <= 6 ? 3.0 : 4.0));
+                const double fp = std::ceil(busy / 4.0) * 2.0 * v.cb * pq;
+                const double cost = passes * (std::max(smem, fp) + 1.0);
+                if (best < 0 || cost < best) { best = cost; c->dct_var = (int)i; c->dct_pq = pq; }
+            }
         }
+        if (env_int("SRFE_DCT_CB", 0) > 0)                             // developer override (tuning only)
+            for (size_t i = 0; i < e->dct_vars.size(); ++i) if (e->dct_vars[i].cb == env_int("SRFE_DCT_CB", 0)) c->dct_var = (int)i;
+        if (env_int("SRFE_DCT_PQ", 0) > 0) c->dct_pq = std::min(2, env_int("SRFE_DCT_PQ", 0));
         blob = align16(e->blob_common + e->dct_vars[c->dct_var].bytes);
     }
     c->blob = blob;
@@ -327,7 +339,7 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
 // warps resident as the shared-memory budget allows, prefer two CTAs per SM (their phases overlap).
 static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Config* out) {
     double best = -1.0;
-    Config bc{0, 0, 1, 0, 0, 0, 0, 0, -1};
+    Config bc{0, 0, 1, 0, 0, 0, 0, 0, -1, 1};
     int cpc_max = (e->family == FAM_MFCC) ? 1 : 8;
     if (8.0 * kp.T * kp.T >= 4294967296.0) cpc_max = 1;              // magic division range (frame_pos)
     const int per_sm = 228 * 1024;                                   // B200: 228 KB per SM, 1 KB reserved per CTA
@@ -387,7 +399,7 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     if (cfg.dct_var >= 0) {
         const Entry::DctVar& v = e->dct_vars[cfg.dct_var];
         kp.blob_bytes = e->blob_common;
-        kp.dct_cb = v.cb; kp.dct_nbe = v.nbe; kp.dct_nbo = v.nbo;
+        kp.dct_cb = v.cb; kp.dct_pq = cfg.dct_pq; kp.dct_nbe = v.nbe; kp.dct_nbo = v.nbo;
         kp.dct_src = v.off; kp.dct_bytes = v.bytes; kp.off_dfold = e->blob_common;
     }
     kp.sm_ctile = cfg.ctile_off;

@@ -10,7 +10,9 @@
 //   z[m] = xw[2m] + i xw[2m+1]           M = N/2 complex points, V = M/16 per lane
 //   pass 1   lane l: DFT-V over m = l + 16 j        (registers)
 //   twiddle  W_M^{l k1}                              (scalar table in shared memory, broadcast operand)
-//   exchange through a padded shared-memory tile     (one 16-byte C2 per point: STS.128 / LDS.128)
+//   exchange through a padded shared-memory tile     (re and im in separate 8-byte planes: STS.64 / LDS.64 --
+//                                                     measured on B200, LDS.128 delivers 64 B/clk/SM, LDS.64 128 B/clk/SM,
+//                                                     scripts/ubench/lds_issue.cu)
 //   pass 2   M=256: one DFT-16 per lane              (registers)
 //            M=320: DFT-16 = two radix-4 passes with a second (skewed) exchange
 //   Z[k] -> shared, natural order
@@ -136,12 +138,12 @@ SRFE_HD void dft20(C2* v) {
 template <int NFFT> struct FftGeom;
 template <> struct FftGeom<512> {
     static constexpr int N = 512, M = 256, L = 16, V = 16;
-    static constexpr int XS = 17;                 // exchange row stride (C2 units): odd -> LDS.128 conflict-free
+    static constexpr int XS = 17;                 // exchange row stride (points): odd -> the 16 lanes hit 16 bank pairs
     static constexpr int SCRATCH_C2 = 16 * 17;    // >= M (zbuf) and >= (M + 1 + 16) / 2 (packed power buffer)
 };
 template <> struct FftGeom<640> {
     static constexpr int N = 640, M = 320, L = 16, V = 20;
-    static constexpr int XS = 20;                 // = 4 (mod 8): both radix-4 gathers conflict-free
+    static constexpr int XS = 20;                 // = 4 (mod 16): both radix-4 gathers conflict-free
     static constexpr int SCRATCH_C2 = 20 * 20;
 };
 
@@ -155,16 +157,30 @@ struct FftTables {
     const cpx* tw16;
 };
 
+// ---- exchange tile: point idx has its real part at plane[idx], its imaginary part at plane[SCRATCH_C2 + idx] ----
+template <int NFFT> SRFE_HD void xst(C2* xbuf, int idx, const C2& v) {
+    P2* pl = reinterpret_cast<P2*>(xbuf);
+    pl[idx] = v.re;
+    pl[FftGeom<NFFT>::SCRATCH_C2 + idx] = v.im;
+}
+template <int NFFT> SRFE_HD C2 xld(const C2* xbuf, int idx) {
+    const P2* pl = reinterpret_cast<const P2*>(xbuf);
+    C2 v;
+    v.re = pl[idx];
+    v.im = pl[FftGeom<NFFT>::SCRATCH_C2 + idx];
+    return v;
+}
+
 // ---- phase 1: DFT-V, twiddle, scatter into the exchange tile (row k1, column l) --------
 template <int NFFT>
 SRFE_HD void fft_phase1(C2* v, int l, C2* xbuf, const FftTables& T) {
     typedef FftGeom<NFFT> G;
     if (G::V == 16) dft16(v); else dft20(v);
-    xbuf[l] = v[0];
+    xst<NFFT>(xbuf, l, v[0]);
 #pragma unroll
     for (int k1 = 1; k1 < G::V; ++k1) {
         const cpx w = T.tw1[k1 * 16 + l];
-        xbuf[k1 * G::XS + l] = cmuls(v[k1], w.x, w.y);
+        xst<NFFT>(xbuf, k1 * G::XS + l, cmuls(v[k1], w.x, w.y));
     }
 }
 
@@ -172,7 +188,7 @@ SRFE_HD void fft_phase1(C2* v, int l, C2* xbuf, const FftTables& T) {
 SRFE_HD void fft_phase2_512(int l, const C2* xbuf, C2* v) {
     typedef FftGeom<512> G;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = xbuf[l * G::XS + i];
+    for (int i = 0; i < 16; ++i) v[i] = xld<512>(xbuf, l * G::XS + i);
     dft16(v);                                   // v[k2] = Z[l + 16 k2]
 }
 SRFE_HD void fft_store_z_512(int l, const C2* v, C2* zbuf) {
@@ -187,9 +203,9 @@ SRFE_HD void fft_phase2_640(int lane, const C2* xbuf, C2* v, const FftTables& T)
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const C2* row = xbuf + (b + 4 * i) * G::XS + a;
+        const int row = (b + 4 * i) * G::XS + a;
 #pragma unroll
-        for (int l2 = 0; l2 < 4; ++l2) v[4 * i + l2] = row[4 * l2];
+        for (int l2 = 0; l2 < 4; ++l2) v[4 * i + l2] = xld<640>(xbuf, row + 4 * l2);
         dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);      // index = k2a
     }
     const cpx t1 = T.tw16[a * 4 + 1], t2 = T.tw16[a * 4 + 2], t3 = T.tw16[a * 4 + 3];
@@ -201,14 +217,14 @@ SRFE_HD void fft_phase2_640(int lane, const C2* xbuf, C2* v, const FftTables& T)
     }
 }
 // second exchange: element (l1 = a, k2a = c) of row k1 lives at column 4 c + ((a + c) & 3)
-// (skewed so that the 8-lane phases of both the scatter and the gather hit 8 distinct 16-byte banks)
+// (skewed so that the 16 lanes of both the scatter and the gather hit 16 distinct bank pairs)
 SRFE_HD void fft_scatter2_640(int lane, const C2* v, C2* xbuf) {
     typedef FftGeom<640> G;
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xbuf[(b + 4 * i) * G::XS + 4 * c + ((a + c) & 3)] = v[4 * i + c];
+        for (int c = 0; c < 4; ++c) xst<640>(xbuf, (b + 4 * i) * G::XS + 4 * c + ((a + c) & 3), v[4 * i + c]);
 }
 // pass 3: lane = c + 4 b handles k2a = c, k1 = b + 4 i; DFT-4 over l1 -> k2b;
 // v[4 i + k2b] = Z[k1 + 20 (c + 4 k2b)]
@@ -217,9 +233,9 @@ SRFE_HD void fft_phase3_640(int lane, const C2* xbuf, C2* v) {
     const int c = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const C2* row = xbuf + (b + 4 * i) * G::XS + 4 * c;
+        const int row = (b + 4 * i) * G::XS + 4 * c;
 #pragma unroll
-        for (int l1 = 0; l1 < 4; ++l1) v[4 * i + l1] = row[(l1 + c) & 3];
+        for (int l1 = 0; l1 < 4; ++l1) v[4 * i + l1] = xld<640>(xbuf, row + ((l1 + c) & 3));
         dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
 }

@@ -59,7 +59,7 @@ struct KParams {
     float top_db, amin, dct_row0_sum;
     const float* dct_kf;               // global [n_mfcc][n_mels] DCT-II rows (generic path, odd n_mels)
     int dct_fold, off_dfold;           // folded DCT table: shared-memory offset (right after the common tables)
-    int dct_cb, dct_nbe, dct_nbo;      //   coefficients per block, even / odd block counts
+    int dct_cb, dct_pq, dct_nbe, dct_nbo;   //   coefficients per block, frame pairs per thread, even / odd block counts
     int dct_src, dct_bytes;            //   where the chosen block-size variant sits in the global blob
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
@@ -241,52 +241,67 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 
 // --------------------------------------------------------------------------------
 // folded DCT-II on the FP32 pipe (see the epilogue comment in the kernel)
-//   work item = (block of CB same-parity coefficients, frame pair); one THREAD per item, items dealt over the whole
-//   CTA, so every warp is busy and nothing is combined across lanes.  Per f the thread reads its pair's folded value
-//   (LDS.64) and its block's CB coefficients (one or two LDS.128, the same address for all lanes of a block) and
-//   issues CB FFMA2.  Table layout: [block][f < n/2][RW] floats, RW = 4 (CB <= 4) or 8, even-k blocks first.
-//   The host picks CB so that the items fill one pass of the CTA (srfe_abi.cu: smem_plan).
+//   work item = (block of CB same-parity coefficients, PQ frame pairs); one THREAD per item, items dealt over the
+//   whole CTA, nothing is combined across lanes.  Per f the thread reads its pairs' folded values (PQ LDS.64) and its
+//   block's CB coefficients (LDS.128 [+ LDS], the same address for all lanes of a block) and issues PQ CB FFMA2.
+//   Table layout: [block][f < n/2][RW] floats, RW = 4 (CB <= 4) or 8, even-k blocks first.
+//   The phase is bound by shared-memory wavefronts or by FFMA2 issue depending on the tile; the host picks (CB, PQ)
+//   from a small cost model (srfe_abi.cu: smem_plan).
 //   Measured alternatives, all slower: warp tasks of 4 coefficients x 64 pairs with the f range split over half-warps
 //   (10 tasks for 13-14 warps, ~550 instructions of per-task set-up / shuffle combine / stores against 512 FFMA2);
 //   5-coefficient blocks with shared-memory atomics; the table read through L1 from global memory.
 // --------------------------------------------------------------------------------
-template <int CB>
+template <int CB, int PQ>
 __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, const float* dtab, const P2* fmeanP,
                                           float* ctile, float thr, int npairs, int TC, int tid, int nthr) {
     constexpr int RW = CB <= 4 ? 4 : 8;
     const int half = p.n_filt >> 1, TSP = p.tile_stride;
-    const int nitems = (p.dct_nbe + p.dct_nbo) * npairs;
+    const int nq = (npairs + PQ - 1) / PQ;                              // a thread's pairs: q, q + nq, ... (row stride TSP
+    const int nitems = (p.dct_nbe + p.dct_nbo) * nq;                    //  between lanes keeps the LDS.64 conflict-free)
     for (int it = tid; it < nitems; it += nthr) {
-        const int b = it / npairs, q = it - b * npairs;
+        const int b = it / nq, q0 = it - b * nq;
         const int par = b >= p.dct_nbe ? 1 : 0;
-        const P2* x = tileP + q * TSP + par * half;                    // s[0..half) then d[0..half), both ascending
-        const float4* d = reinterpret_cast<const float4*>(dtab) + b * half * (RW / 4);
-        P2 acc[CB];
+        const P2* x[PQ];
 #pragma unroll
-        for (int j = 0; j < CB; ++j) acc[j] = bc(0.f);
+        for (int i = 0; i < PQ; ++i) x[i] = tileP + min(q0 + i * nq, npairs - 1) * TSP + par * half;   // s[0..half) | d[0..half)
+        const float4* d = reinterpret_cast<const float4*>(dtab) + b * half * (RW / 4);
+        P2 acc[PQ][CB];
+#pragma unroll
+        for (int i = 0; i < PQ; ++i)
+#pragma unroll
+            for (int j = 0; j < CB; ++j) acc[i][j] = bc(0.f);
 #pragma unroll 4
         for (int f = 0; f < half; ++f) {
-            const P2 xv = x[f];
             float c[8];
             const float4 d0 = d[f * (RW / 4)];
             c[0] = d0.x; c[1] = d0.y; c[2] = d0.z; c[3] = d0.w;
             if (RW == 8) { const float4 d1 = d[f * 2 + 1]; c[4] = d1.x; c[5] = d1.y; c[6] = d1.z; c[7] = d1.w; }
 #pragma unroll
-            for (int j = 0; j < CB; ++j) acc[j] = pfma(xv, bc(c[j]), acc[j]);
+            for (int i = 0; i < PQ; ++i) {
+                const P2 xv = x[i][f];
+#pragma unroll
+                for (int j = 0; j < CB; ++j) acc[i][j] = pfma(xv, bc(c[j]), acc[i][j]);
+            }
         }
         const int k0 = 2 * CB * (b - par * p.dct_nbe) + par;
-        if (k0 == 0) {                                                  // put the frame's centre back on c0
-            const P2 cm = fmeanP[q];
-            acc[0] = pfma(mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr)), bc(p.dct_row0_sum), acc[0]);
-        }
-        float* cq = ctile + 2 * q;
-        const bool two = 2 * q + 1 < p.T;
 #pragma unroll
-        for (int j = 0; j < CB; ++j) {
-            const int k = k0 + 2 * j;
-            if (k < p.n_mfcc) {
-                cq[k * TC] = acc[j].lo;
-                if (two) cq[k * TC + 1] = acc[j].hi;
+        for (int i = 0; i < PQ; ++i) {
+            const int q = q0 + i * nq;
+            if (q < npairs) {
+                if (k0 == 0) {                                          // put the frame's centre back on c0
+                    const P2 cm = fmeanP[q];
+                    acc[i][0] = pfma(mkp(fmaxf(cm.lo, thr), fmaxf(cm.hi, thr)), bc(p.dct_row0_sum), acc[i][0]);
+                }
+                float* cq = ctile + 2 * q;
+                const bool two = 2 * q + 1 < p.T;
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    const int k = k0 + 2 * j;
+                    if (k < p.n_mfcc) {
+                        cq[k * TC] = acc[i][j].lo;
+                        if (two) cq[k * TC + 1] = acc[i][j].hi;
+                    }
+                }
             }
         }
     }
@@ -635,14 +650,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 }
                 __syncthreads();
                 // (2) the contraction
-                if (!(p.debug & 2)) switch (p.dct_cb) {
-                    case 2: dct_items<2>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
-                    case 3: dct_items<3>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
-                    case 4: dct_items<4>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
-                    case 5: dct_items<5>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
-                    case 6: dct_items<6>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
-                    default: dct_items<8>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr); break;
+#define SRFE_DCT(CB_, PQ_) dct_items<CB_, PQ_>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr)
+                if (!(p.debug & 2)) switch (p.dct_cb * 4 + p.dct_pq) {
+                    case 2 * 4 + 1: SRFE_DCT(2, 1); break;   case 2 * 4 + 2: SRFE_DCT(2, 2); break;
+                    case 3 * 4 + 1: SRFE_DCT(3, 1); break;   case 3 * 4 + 2: SRFE_DCT(3, 2); break;
+                    case 4 * 4 + 1: SRFE_DCT(4, 1); break;   case 4 * 4 + 2: SRFE_DCT(4, 2); break;
+                    case 5 * 4 + 1: SRFE_DCT(5, 1); break;   case 5 * 4 + 2: SRFE_DCT(5, 2); break;
+                    case 6 * 4 + 1: SRFE_DCT(6, 1); break;   case 6 * 4 + 2: SRFE_DCT(6, 2); break;
+                    case 8 * 4 + 1: SRFE_DCT(8, 1); break;   default:        SRFE_DCT(8, 2); break;
                 }
+#undef SRFE_DCT
             } else {
                 // generic path (odd n_mels): plain packed dot products against the global DCT rows
                 for (int task = tid; task < p.n_mfcc * npairs; task += nthr) {
