@@ -118,7 +118,7 @@ static int add_bank(BlobBuilder& bb, KParams& kp, const SparseBank& sb, int n_ff
         e->mel_code |= (unsigned)(n4 - 1) << (2 * g);
     }
     // the packed power buffer aliases the FFT scratch: the padded runs must stay inside it
-    const int cap = (n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 2;    // P2 slots
+    const int cap = n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2;          // P2 slots
     if (ell.max_reach > cap) return fail(SRFE_ERR_UNSUPPORTED, "filterbank too wide for the shared-memory power buffer");
     kp.off_gm = bb.add(ell.gmeta.data(), ell.gmeta.size() * 4);
     kp.off_fs = bb.add(ell.start.data(), ell.start.size() * 4);
@@ -318,7 +318,9 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
         blob = align16(e->blob_common + e->dct_vars[c->dct_var].bytes);
     }
     c->blob = blob;
-    int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_C2 : FftGeom<640>::SCRATCH_C2) * 16;
+    int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
+    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT)        // CTA-wide [bin][2 hw + 1] transposition tile
+        scratch = std::max(scratch, align16(e->n_bins * (2 * hw + 1) * 4));
     int tile = 0;
     c->ctile_off = blob;
     if (e->family == FAM_MFCC) {

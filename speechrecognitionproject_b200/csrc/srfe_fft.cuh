@@ -10,14 +10,12 @@
 //   z[m] = xw[2m] + i xw[2m+1]           M = N/2 complex points, V = M/16 per lane
 //   pass 1   lane l: DFT-V over m = l + 16 j        (registers)
 //   twiddle  W_M^{l k1}                              (scalar table in shared memory, broadcast operand)
-//   exchange through a padded shared-memory tile     (re and im in separate 8-byte planes: STS.64 / LDS.64 --
-//                                                     measured on B200, LDS.128 delivers 64 B/clk/SM, LDS.64 128 B/clk/SM,
-//                                                     scripts/ubench/lds_issue.cu)
+//   exchange through a padded shared-memory tile     (real parts, then imaginary parts, through the same 8-byte slots)
 //   pass 2   M=256: one DFT-16 per lane              (registers)
 //            M=320: DFT-16 = two radix-4 passes with a second (skewed) exchange
-//   Z[k] -> shared, natural order
-//   untangle lane takes the pairs (k, M-k), k = l + 16 r: one twiddle per pair,
-//            yields 4|X[k]|^2 and 4|X[M-k]|^2 (the 1/4 is folded downstream)
+//   untangle lane takes the pairs (k, M-k): one twiddle per pair, yields 4|X[k]|^2 and 4|X[M-k]|^2 (the 1/4 is
+//            folded downstream); on the device the partner Z[M-k] comes by warp shuffle (srfe_kernels.cuh), the
+//            shared-memory form below serves tests/emu
 //
 // Everything is __host__ __device__ and free of warp intrinsics so tests/emu runs the
 // identical index arithmetic lane by lane on the CPU (phases are separated by warp
@@ -135,16 +133,21 @@ SRFE_HD void dft20(C2* v) {
 }
 
 // ---- geometry of the half-warp FFT ---------------------------------------------------
+// The exchange tile holds ONE 8-byte plane (real parts, then imaginary parts, of both frames) at a time: the two
+// planes go through the same SCRATCH_P2 slots one after the other, so a half-warp needs 2.2 KB (N = 512) / 3.2 KB
+// (N = 640) of shared memory instead of twice that -- which is what lets two MFCC CTAs (each with its per-clip dB
+// tile) share an SM -- and every access is an 8-byte one (LDS.128 delivers half the bandwidth of LDS.64 on B200,
+// scripts/ubench/lds_issue.cu).
 template <int NFFT> struct FftGeom;
 template <> struct FftGeom<512> {
     static constexpr int N = 512, M = 256, L = 16, V = 16;
     static constexpr int XS = 17;                 // exchange row stride (points): odd -> the 16 lanes hit 16 bank pairs
-    static constexpr int SCRATCH_C2 = 16 * 17;    // >= M (zbuf) and >= (M + 1 + 16) / 2 (packed power buffer)
+    static constexpr int SCRATCH_P2 = 16 * 17;    // >= M + 1 + mel padding (packed power buffer)
 };
 template <> struct FftGeom<640> {
     static constexpr int N = 640, M = 320, L = 16, V = 20;
     static constexpr int XS = 20;                 // = 4 (mod 16): both radix-4 gathers conflict-free
-    static constexpr int SCRATCH_C2 = 20 * 20;
+    static constexpr int SCRATCH_P2 = 20 * 20;
 };
 
 // Twiddle tables a CTA keeps in shared memory (built on the host in double):
@@ -157,57 +160,50 @@ struct FftTables {
     const cpx* tw16;
 };
 
-// ---- exchange tile: point idx has its real part at plane[idx], its imaginary part at plane[SCRATCH_C2 + idx] ----
-template <int NFFT> SRFE_HD void xst(C2* xbuf, int idx, const C2& v) {
-    P2* pl = reinterpret_cast<P2*>(xbuf);
-    pl[idx] = v.re;
-    pl[FftGeom<NFFT>::SCRATCH_C2 + idx] = v.im;
-}
-template <int NFFT> SRFE_HD C2 xld(const C2* xbuf, int idx) {
-    const P2* pl = reinterpret_cast<const P2*>(xbuf);
-    C2 v;
-    v.re = pl[idx];
-    v.im = pl[FftGeom<NFFT>::SCRATCH_C2 + idx];
-    return v;
-}
+template <int PLANE> SRFE_HD const P2& plane_of(const C2& c) { return PLANE == 0 ? c.re : c.im; }
+template <int PLANE> SRFE_HD P2& plane_of(C2& c) { return PLANE == 0 ? c.re : c.im; }
 
-// ---- phase 1: DFT-V, twiddle, scatter into the exchange tile (row k1, column l) --------
+// ---- pass 1: DFT-V over m = l + 16 j and the twiddles W_M^{l k1}, all in registers ---------
 template <int NFFT>
-SRFE_HD void fft_phase1(C2* v, int l, C2* xbuf, const FftTables& T) {
+SRFE_HD void fft_pass1(C2* v, int l, const FftTables& T) {
     typedef FftGeom<NFFT> G;
     if (G::V == 16) dft16(v); else dft20(v);
-    xst<NFFT>(xbuf, l, v[0]);
 #pragma unroll
     for (int k1 = 1; k1 < G::V; ++k1) {
         const cpx w = T.tw1[k1 * 16 + l];
-        xst<NFFT>(xbuf, k1 * G::XS + l, cmuls(v[k1], w.x, w.y));
+        v[k1] = cmuls(v[k1], w.x, w.y);
     }
 }
-
-// ---- phase 2 (N=512): one DFT-16 per lane, Z out in natural order ------------------------
-SRFE_HD void fft_phase2_512(int l, const C2* xbuf, C2* v) {
+// ---- first exchange: row k1, column l.  One plane per call; callers separate put / get with a warp sync ----
+template <int NFFT, int PLANE>
+SRFE_HD void xs_put(const C2* v, int l, P2* buf) {
+    typedef FftGeom<NFFT> G;
+#pragma unroll
+    for (int k1 = 0; k1 < G::V; ++k1) buf[k1 * G::XS + l] = plane_of<PLANE>(v[k1]);
+}
+// N = 512: lane l gathers row l (k1 = l), 16 columns -> the inputs of its DFT-16 (output v[k2] = Z[l + 16 k2])
+template <int PLANE>
+SRFE_HD void xs_get_512(int l, const P2* buf, C2* w) {
     typedef FftGeom<512> G;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = xld<512>(xbuf, l * G::XS + i);
-    dft16(v);                                   // v[k2] = Z[l + 16 k2]
-}
-SRFE_HD void fft_store_z_512(int l, const C2* v, C2* zbuf) {
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) zbuf[l + 16 * k2] = v[k2];
+    for (int i = 0; i < 16; ++i) plane_of<PLANE>(w[i]) = buf[l * G::XS + i];
 }
 
-// ---- phases 2/3 (N=640): DFT-16 over l = l1 + 4 l2 as two radix-4 passes -----------------
-// lane = a + 4 b.  pass 2: l1 = a, k1 = b + 4 i (i<5), DFT-4 over l2 -> k2a.
-SRFE_HD void fft_phase2_640(int lane, const C2* xbuf, C2* v, const FftTables& T) {
+// ---- N = 640: DFT-16 over l = l1 + 4 l2 as two radix-4 passes ----------------------------------
+// lane = a + 4 b.  pass 2: l1 = a, k1 = b + 4 i (i<5), DFT-4 over l2 -> k2a, then the W_16^{a k2a} twiddles.
+template <int PLANE>
+SRFE_HD void xs_get2_640(int lane, const P2* buf, C2* w) {
     typedef FftGeom<640> G;
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int row = (b + 4 * i) * G::XS + a;
+    for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int l2 = 0; l2 < 4; ++l2) v[4 * i + l2] = xld<640>(xbuf, row + 4 * l2);
-        dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);      // index = k2a
-    }
+        for (int l2 = 0; l2 < 4; ++l2) plane_of<PLANE>(w[4 * i + l2]) = buf[(b + 4 * i) * G::XS + a + 4 * l2];
+}
+SRFE_HD void fft_pass2_640(int lane, C2* v, const FftTables& T) {
+    const int a = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);      // index = k2a
     const cpx t1 = T.tw16[a * 4 + 1], t2 = T.tw16[a * 4 + 2], t3 = T.tw16[a * 4 + 3];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -218,26 +214,35 @@ SRFE_HD void fft_phase2_640(int lane, const C2* xbuf, C2* v, const FftTables& T)
 }
 // second exchange: element (l1 = a, k2a = c) of row k1 lives at column 4 c + ((a + c) & 3)
 // (skewed so that the 16 lanes of both the scatter and the gather hit 16 distinct bank pairs)
-SRFE_HD void fft_scatter2_640(int lane, const C2* v, C2* xbuf) {
+template <int PLANE>
+SRFE_HD void xs_put3_640(int lane, const C2* v, P2* buf) {
     typedef FftGeom<640> G;
     const int a = lane & 3, b = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xst<640>(xbuf, (b + 4 * i) * G::XS + 4 * c + ((a + c) & 3), v[4 * i + c]);
+        for (int c = 0; c < 4; ++c) buf[(b + 4 * i) * G::XS + 4 * c + ((a + c) & 3)] = plane_of<PLANE>(v[4 * i + c]);
 }
 // pass 3: lane = c + 4 b handles k2a = c, k1 = b + 4 i; DFT-4 over l1 -> k2b;
 // v[4 i + k2b] = Z[k1 + 20 (c + 4 k2b)]
-SRFE_HD void fft_phase3_640(int lane, const C2* xbuf, C2* v) {
+template <int PLANE>
+SRFE_HD void xs_get3_640(int lane, const P2* buf, C2* w) {
     typedef FftGeom<640> G;
     const int c = lane & 3, b = lane >> 2;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int row = (b + 4 * i) * G::XS + 4 * c;
+    for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int l1 = 0; l1 < 4; ++l1) v[4 * i + l1] = xld<640>(xbuf, row + ((l1 + c) & 3));
-        dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
+        for (int l1 = 0; l1 < 4; ++l1) plane_of<PLANE>(w[4 * i + l1]) = buf[(b + 4 * i) * G::XS + 4 * c + ((l1 + c) & 3)];
+}
+SRFE_HD void fft_pass3_640(C2* v) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dft4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// ---- Z in natural order (tests/emu only: the kernels untangle straight from registers with shuffles) ----
+SRFE_HD void fft_store_z_512(int l, const C2* v, C2* zbuf) {
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) zbuf[l + 16 * k2] = v[k2];
 }
 SRFE_HD void fft_store_z_640(int lane, const C2* v, C2* zbuf) {
     const int c = lane & 3, b = lane >> 2;

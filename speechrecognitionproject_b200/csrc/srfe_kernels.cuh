@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const int2* g_meta = reinterpret_cast<const int2*>(smem + p.off_gm);
     const int* f_start = reinterpret_cast<const int*>(smem + p.off_fs);
     const float2* f_w2 = reinterpret_cast<const float2*>(smem + p.off_fw4);     // [step][plane][lane]: two LDS.64 per step
-    C2* scratch_all = reinterpret_cast<C2*>(smem + p.sm_scratch);
+    P2* scratch_all = reinterpret_cast<P2*>(smem + p.sm_scratch);
     float* tile = reinterpret_cast<float*>(smem + p.sm_tile);
     // MFCC only: the per-clip dB tile holds one row per frame PAIR, each element an (A, B) pair -- exactly what the
     // mel stage produces and what the packed DCT consumes; row stride p.tile_stride (P2 units, odd); +1 dummy row
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     __syncthreads();
 
     const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
-    C2* xb = scratch_all + hw * G::SCRATCH_C2;
+    P2* xb = scratch_all + hw * G::SCRATCH_P2;           // this half-warp's exchange tile / packed power buffer
 
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
         const int clip0 = grp * p.cpc;
@@ -389,17 +389,32 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 }
                 C2 v[G::V];
                 window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
-                fft_phase1<NFFT>(v, l, xb, T);
+                // The two planes of every exchange pass through the same slots: put / sync / get, twice.
+                fft_pass1<NFFT>(v, l, T);
+                C2 w[G::V];
+                __syncwarp();                               // the previous pair's readers are done with the tile
+                xs_put<NFFT, 0>(v, l, xb);
+                __syncwarp();
+                if (NFFT == 512) xs_get_512<0>(l, xb, w); else xs_get2_640<0>(l, xb, w);
+                __syncwarp();
+                xs_put<NFFT, 1>(v, l, xb);
                 __syncwarp();
                 if (NFFT == 512) {
-                    fft_phase2_512(l, xb, v);
-                    pmid = fft_untangle_512_shfl(l, lane, v, T, pa, pb);
+                    xs_get_512<1>(l, xb, w);
+                    dft16(w);                               // w[k2] = Z[l + 16 k2]
+                    pmid = fft_untangle_512_shfl(l, lane, w, T, pa, pb);
                 } else {
-                    fft_phase2_640(l, xb, v, T);
+                    xs_get2_640<1>(l, xb, w);
+                    fft_pass2_640(l, w, T);
                     __syncwarp();
-                    fft_scatter2_640(l, v, xb);
+                    xs_put3_640<0>(l, w, xb);
                     __syncwarp();
-                    fft_phase3_640(l, xb, v);
+                    xs_get3_640<0>(l, xb, v);
+                    __syncwarp();
+                    xs_put3_640<1>(l, w, xb);
+                    __syncwarp();
+                    xs_get3_640<1>(l, xb, v);
+                    fft_pass3_640(v);
                     pmid = fft_untangle_640_shfl(l, lane, v, T, pa, pb);
                 }
 
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                     if (p.layout == SRFE_LAYOUT_TF) {
                         float* rowA = p.out + ((long long)(clip0 + cA.c) * p.T + cA.t) * F;
                         float* rowB = p.out + ((long long)(clip0 + cB.c) * p.T + cB.t) * F;
-                        P2* pbuf = reinterpret_cast<P2*>(xb);       // N = 640 only: re-order through shared memory
+                        P2* pbuf = xb;                              // N = 640 only: re-order through shared memory
 #pragma unroll
                         for (int r = 0; r < G::M / 32; ++r) {
                             const int k = kbin(r);
@@ -491,7 +506,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 } else {
                     // power -> shared as (A, B) pairs (aliases the FFT scratch), then sparse triangular sums:
                     // 16-filter groups with a uniform trip count (ELL), weights as float4 runs
-                    P2* pbuf = reinterpret_cast<P2*>(xb);
+                    P2* pbuf = xb;
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < G::M / 32; ++r) {

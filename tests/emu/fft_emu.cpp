@@ -25,27 +25,37 @@ static void run(const float* xa, const float* xb, float* pa_out, float* pb_out) 
     T.twu = reinterpret_cast<const cpx*>(twu.data());
     T.tw16 = reinterpret_cast<const cpx*>(tw16.data());
 
-    std::vector<C2> scratch(G::SCRATCH_C2);
-    static C2 v[16][G::V];
+    std::vector<P2> xs(G::SCRATCH_P2);            // the exchange tile: one plane at a time, as on the device
+    std::vector<C2> zbuf(G::M);
+    static C2 v[16][G::V], w[16][G::V];
     for (int l = 0; l < 16; ++l)
         for (int j = 0; j < G::V; ++j) {
             const int m = l + 16 * j;
             v[l][j].re = mkp(xa[2 * m], xb[2 * m]);
             v[l][j].im = mkp(xa[2 * m + 1], xb[2 * m + 1]);
         }
-    for (int l = 0; l < 16; ++l) fft_phase1<NFFT>(v[l], l, scratch.data(), T);
+    for (int l = 0; l < 16; ++l) fft_pass1<NFFT>(v[l], l, T);
     if (NFFT == 512) {
-        for (int l = 0; l < 16; ++l) fft_phase2_512(l, scratch.data(), v[l]);
-        for (int l = 0; l < 16; ++l) fft_store_z_512(l, v[l], scratch.data());
+        for (int l = 0; l < 16; ++l) xs_put<NFFT, 0>(v[l], l, xs.data());
+        for (int l = 0; l < 16; ++l) xs_get_512<0>(l, xs.data(), w[l]);
+        for (int l = 0; l < 16; ++l) xs_put<NFFT, 1>(v[l], l, xs.data());
+        for (int l = 0; l < 16; ++l) xs_get_512<1>(l, xs.data(), w[l]);
+        for (int l = 0; l < 16; ++l) { dft16(w[l]); fft_store_z_512(l, w[l], zbuf.data()); }
     } else {
-        for (int l = 0; l < 16; ++l) fft_phase2_640(l, scratch.data(), v[l], T);
-        for (int l = 0; l < 16; ++l) fft_scatter2_640(l, v[l], scratch.data());
-        for (int l = 0; l < 16; ++l) fft_phase3_640(l, scratch.data(), v[l]);
-        for (int l = 0; l < 16; ++l) fft_store_z_640(l, v[l], scratch.data());
+        for (int l = 0; l < 16; ++l) xs_put<NFFT, 0>(v[l], l, xs.data());
+        for (int l = 0; l < 16; ++l) xs_get2_640<0>(l, xs.data(), w[l]);
+        for (int l = 0; l < 16; ++l) xs_put<NFFT, 1>(v[l], l, xs.data());
+        for (int l = 0; l < 16; ++l) xs_get2_640<1>(l, xs.data(), w[l]);
+        for (int l = 0; l < 16; ++l) fft_pass2_640(l, w[l], T);
+        for (int l = 0; l < 16; ++l) xs_put3_640<0>(l, w[l], xs.data());
+        for (int l = 0; l < 16; ++l) xs_get3_640<0>(l, xs.data(), v[l]);
+        for (int l = 0; l < 16; ++l) xs_put3_640<1>(l, w[l], xs.data());
+        for (int l = 0; l < 16; ++l) xs_get3_640<1>(l, xs.data(), v[l]);
+        for (int l = 0; l < 16; ++l) { fft_pass3_640(v[l]); fft_store_z_640(l, v[l], zbuf.data()); }
     }
     for (int l = 0; l < 16; ++l) {
         P2 pa[G::M / 32], pb[G::M / 32];
-        const P2 pmid = fft_untangle<NFFT>(l, scratch.data(), T, pa, pb);
+        const P2 pmid = fft_untangle<NFFT>(l, zbuf.data(), T, pa, pb);
         for (int r = 0; r < G::M / 32; ++r) {
             const int k = l + 16 * r;
             pa_out[k] = 0.25f * pa[r].lo;           pb_out[k] = 0.25f * pa[r].hi;
