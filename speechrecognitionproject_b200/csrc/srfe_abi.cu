@@ -355,15 +355,18 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 if (cpc > 1 && cpc > kp.n_clips) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
-                // Fitted to scripts/tune.py sweeps on the B200: throughput ~ round efficiency x (resident warps - 2.3)^0.8;
-                // for MFCC (CTA barriers + serial epilogue) two co-resident CTAs are worth ~1.6x one CTA at equal warps,
-                // for SPEC / FBANK (no barriers) the CTA count does not matter.
-                // The FT spectrogram tile (one CTA barrier per round) wants exactly filled rounds and few clips per group.
+                // Fitted to scripts/tune.py sweeps on the B200 (profiles/r1_notes.md): throughput ~ round efficiency x
+                // (resident warps - 2.3)^0.8.  Kernels with CTA barriers (MFCC epilogue, FT spectrogram tile) gain from a
+                // second co-resident CTA whose frame phase fills the first one's serial phase (MFCC ~1.6x at equal warps,
+                // and partly filled rounds then cost half as much); barrier-free kernels (TF spectrogram, FBANK) prefer
+                // one wide CTA and many clips per group (fewer group prologues).
                 const bool ft = e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT;
-                double score = (double)nf / (double)(rounds * per_round);
-                score *= std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), ft ? 0.5 : 0.8);
-                if (ctas == 2) score *= (e->family == FAM_MFCC) ? 1.6 : 1.02;
-                score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 - 0.004 * (cpc - 1);
+                const bool mf = e->family == FAM_MFCC;
+                double eff = (double)nf / (double)(rounds * per_round);
+                if (mf && ctas == 2) eff = std::sqrt(eff);
+                double score = eff * std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
+                if (ctas == 2) score *= mf ? 1.6 : ft ? 1.1 : 0.96;
+                score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 + 0.01 * std::log2((double)cpc);
                 if (score > best + 1e-9) { best = score; bc = pl; bc.warps = warps; bc.ctas = ctas; bc.cpc = cpc; }
             }
         }
