@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -61,6 +61,9 @@ class ClockSampler:
                 self.rows.append((time.time(), line.strip()))
         self.thr = threading.Thread(target=pump, daemon=True)
         self.thr.start()
+        t_wait = time.time()
+        while not self.rows and time.time() - t_wait < 5.0:      # nvidia-smi takes a moment to print its first row;
+            time.sleep(0.02)                                     # short timed regions must still see samples under load
 
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:

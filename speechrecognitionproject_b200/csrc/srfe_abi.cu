@@ -303,7 +303,7 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
         for (size_t i = 0; i < e->dct_vars.size(); ++i) {
             const Entry::DctVar& v = e->dct_vars[i];
             for (int pq = 1; pq <= 2; ++pq) {
-                const long long items = (long long)(v.nbe + v.nbo) * ((npairs + pq - 1) / pq);
+                const long long items = (long long)(v.nbe + v.nbo) * ((((npairs + pq - 1) / pq) + 15) / 16 * 16);   // half-warp padded
                 const long long passes = (items + nthr - 1) / nthr;
                 const double busy = std::min((double)items / passes, (double)nthr) / 32.0;      // warps per pass
                 const double smem = busy * (2.0 * pq + (v.cb <= 4 ? 2.0 : v.cb <= 6 ? 3.0 : 4.0));

@@ -257,9 +257,11 @@ __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, con
     constexpr int RW = CB <= 4 ? 4 : 8;
     const int half = p.n_filt >> 1, TSP = p.tile_stride;
     const int nq = (npairs + PQ - 1) / PQ;                              // a thread's pairs: q, q + nq, ... (row stride TSP
-    const int nitems = (p.dct_nbe + p.dct_nbo) * nq;                    //  between lanes keeps the LDS.64 conflict-free)
+    const int nqp = (nq + 15) & ~15;                                    //  between lanes keeps the LDS.64 conflict-free);
+    const int nitems = (p.dct_nbe + p.dct_nbo) * nqp;                   // a half-warp never straddles two blocks
     for (int it = tid; it < nitems; it += nthr) {
-        const int b = it / nq, q0 = it - b * nq;
+        const int b = it / nqp, q0 = it - b * nqp;
+        if (q0 >= nq) continue;
         const int par = b >= p.dct_nbe ? 1 : 0;
         const P2* x[PQ];
 #pragma unroll
