@@ -202,7 +202,6 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.hop = p.hop;
     e->kp.start0 = -(p.n_fft / 2);
     e->kp.n_mfcc = p.n_mfcc;
-    e->kp.n_mfcc_pad = (p.n_mfcc + 3) & ~3;
     e->kp.n_deltas = p.n_deltas;
     e->kp.top_db = p.top_db;
     e->kp.amin = p.amin;
@@ -409,7 +408,6 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     }
     kp.sm_ctile = cfg.ctile_off;
     kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
-    kp.sw_prefetch = env_int("SRFE_SWPF", 0);                        // measured: no effect (loads are not the limiter)
     kp.debug = env_int("SRFE_DEBUG", 0);
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;

@@ -8,20 +8,20 @@
 // so that cpc*T fills whole rounds of 2*HW frames.
 //
 //   global PCM --LDG.64, coalesced (16 lanes x 8 B = one 128 B line per load; the
-//                2-2.5x frame overlap is served by L1/L2, HBM sees each sample once);
-//                the NEXT pair of the half-warp is fetched into registers while the
-//                current one is in its output stage (software pipelining)
+//                2-2.5x frame overlap is served by L1/L2, HBM sees each sample once)
 //     -> pre-emphasis (fbank, exact fp32 rounding) -> window (shared table)
-//     -> packed half-warp FFT (registers + one/two shared-memory exchanges); the window
-//        extent [32 JLO, 32 JHI) is a template parameter, so the zero inputs of the
-//        400-in-512 frames are constant-folded out of the first pass
-//     -> untangle -> power (both frames at once)
-//     -> SPEC : scale, ln(. + eps)              -> global (TF) or per-warp 4-frame staging (FT)
+//     -> packed half-warp FFT (registers + one/two shared-memory exchanges, real and imaginary
+//        planes one after the other through the same 8-byte slots); the window extent
+//        [32 JLO, 32 JHI) is a template parameter, so the zero inputs of the 400-in-512
+//        frames are constant-folded out of the first pass
+//     -> untangle (mirror bins by warp shuffle) -> power (both frames at once)
+//     -> SPEC : scale, ln(. + eps)              -> global (TF) or a CTA-wide [bin][frame] tile (FT)
 //        FBANK: sparse triangle sums (uniform-trip ELL), 20 log10 -> global [T][nfilt]
 //        MFCC : sparse Slaney sums, 10 log10    -> per-clip dB tile in shared memory
-//   MFCC epilogue (CTA barrier): clip max -> top_db clamp -> DCT-II (packed FFMA2 with the
-//   even/odd symmetry fold; the legacy mma.sync TF32 path measured slower at fp32 accuracy)
-//   -> np.gradient deltas -> coalesced store.  Only final features reach HBM.
+//   MFCC epilogue (CTA barrier): clip max -> top_db clamp, re-centre, fold -> DCT-II in packed
+//   FFMA2, one thread per (coefficient block, frame pairs) item -> np.gradient deltas ->
+//   coalesced store.  Only final features reach HBM.  Two MFCC CTAs share an SM so that one's
+//   epilogue overlaps the other's frame phase.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -44,7 +44,6 @@ struct KParams {
     int T, hop, start0;
     int cpc, n_groups;                 // clips per group, number of groups
     unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
-    int sw_prefetch;                   // issue prefetch.global.L1 for the next frame pair
     int debug;                         // developer switches (timing experiments only): 1 = skip the MFCC epilogue
     int sm_ctile;                      // coefficient tile offset (aliases the FFT scratch)
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
@@ -55,7 +54,7 @@ struct KParams {
     float scale, log_eps;
     int take_log, layout;
     float preemph;
-    int n_mfcc, n_mfcc_pad, n_deltas;
+    int n_mfcc, n_deltas;
     float top_db, amin, dct_row0_sum;
     const float* dct_kf;               // global [n_mfcc][n_mels] DCT-II rows (generic path, odd n_mels)
     int dct_fold, off_dfold;           // folded DCT table: shared-memory offset (right after the common tables)
@@ -63,7 +62,7 @@ struct KParams {
     int dct_src, dct_bytes;            //   where the chosen block-size variant sits in the global blob
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
-    int w_lo, w_hi;                    // non-zero extent of the window (informational)
+    int w_lo, w_hi;                    // non-zero extent of the window (host: picks the JLO / JHI instantiation)
 };
 
 // --------------------------------------------------------------------------------
@@ -93,18 +92,6 @@ __device__ __forceinline__ float edge_sample(const KParams& p, const S* __restri
         return __fsub_rn(ld1<S>(x + idx), __fmul_rn(p.preemph, prev));   // model_fbanks_cnn.py:20 (float32)
     }
     return (idx >= 0 && idx < p.n_samples) ? ld1<S>(x + idx) : 0.f;
-}
-
-// software prefetch of a frame's cache lines (no registers held): lane l touches line l (and l + 16)
-template <int NFFT, typename S>
-__device__ __forceinline__ void prefetch_frame(const S* __restrict__ x, int base, int n_samples, int l) {
-    constexpr int LINES = (NFFT * (int)sizeof(S) + 127) / 128 + 1;      // + 1: frames start mid-line in general
-    const int lo = max(base, 0), hi = min(base + NFFT, n_samples) - 1;
-#pragma unroll
-    for (int i = 0; i < (LINES + 15) / 16; ++i) {
-        const int idx = lo + (l + 16 * i) * (128 / (int)sizeof(S));
-        if (idx <= hi) asm volatile("prefetch.global.L1 [%0];" :: "l"(x + idx));
-    }
 }
 
 template <int FAM, int NJ>
@@ -317,7 +304,6 @@ __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, con
 template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
-    constexpr bool PF = false;                              // register prefetch of the next pair: spills at 128 regs, no gain at 168
     typedef FftGeom<NFFT> G;
     constexpr int NJ = JHI - JLO;
     constexpr int F = G::M + 1;
@@ -364,31 +350,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
         const int rounds = (npairs + HW - 1) / HW;
         float run_max = -CUDART_INF_F;
 
-        RawFrame<FAM, NJ> rawA, rawB;
-        FramePos pA = frame_pos(2 * hw, nf, p.T, p.t_magic, p.cpc), pB = frame_pos(2 * hw + 1, nf, p.T, p.t_magic, p.cpc);
-        if (PF && (hw & ~1) < npairs) {
-            fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-            fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
-        }
-
         for (int it = 0; it < rounds; ++it) {
             const int q = it * HW + hw;
             P2 pa[G::M / 32], pb[G::M / 32], pmid;
             const bool active = (it * HW + (hw & ~1)) < npairs;
             if (active) {                                   // warp-uniform: both half-warps of a warp run together
-                if (!PF) {
-                    pA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc);
-                    pB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
-                    fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-                    fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
-                }
-                const FramePos cA = pA, cB = pB;
-                if (!PF && p.sw_prefetch) {                 // warm L1/L2 with the half-warp's next pair
-                    const int qn = q + HW;
-                    const FramePos nA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc), nB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
-                    if (nA.ok) prefetch_frame<NFFT, SAMP>(pcm + (long long)(clip0 + nA.c) * p.clip_stride, p.start0 + nA.t * p.hop, p.n_samples, l);
-                    if (nB.ok) prefetch_frame<NFFT, SAMP>(pcm + (long long)(clip0 + nB.c) * p.clip_stride, p.start0 + nB.t * p.hop, p.n_samples, l);
-                }
+                // (holding the NEXT pair in registers while this one is transformed was measured: it spills at
+                //  128 registers and gains nothing at 168 / 12 warps; prefetch.global.L1 has no effect either)
+                RawFrame<FAM, NJ> rawA, rawB;
+                const FramePos cA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc), cB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
+                fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cA.c) * p.clip_stride, p.start0 + cA.t * p.hop, l, rawA);
+                fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cB.c) * p.clip_stride, p.start0 + cB.t * p.hop, l, rawB);
                 C2 v[G::V];
                 window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
                 // The two planes of every exchange pass through the same slots: put / sync / get, twice.
@@ -423,16 +395,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 // bin held in slot r of this lane (and its mirror M - k): natural stride-16 order for N = 512,
                 // the radix-4 order of bin640() for N = 640
                 auto kbin = [&](int r) { return NFFT == 512 ? l + 16 * r : bin640(l, r); };
-
-                if (PF) {   // prefetch the half-warp's next pair while this one goes through its output stage
-                    const int qn = q + HW;
-                    pA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc);
-                    pB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
-                    if (((it + 1) * HW + (hw & ~1)) < npairs) {
-                        fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pA.c) * p.clip_stride, p.start0 + pA.t * p.hop, l, rawA);
-                        fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + pB.c) * p.clip_stride, p.start0 + pB.t * p.hop, l, rawB);
-                    }
-                }
 
                 if (FAM == FAM_SPEC) {
                     // density scaling, one-sided doubling (not DC / Nyquist), optional ln(. + eps)
