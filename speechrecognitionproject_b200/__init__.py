@@ -3,7 +3,8 @@ a drop-in for the feature hot path of remit0/SpeechRecognitionProject.
 
 Public surface: :mod:`speechrecognitionproject_b200.features` (reference-named
 functions and batched ops over the C ABI of ``include/srfe.h``) and
-:func:`speechrecognitionproject_b200.patch.patch_model`.
+:func:`speechrecognitionproject_b200.patch.patch_model` (with
+:class:`~speechrecognitionproject_b200.patch.SharedFrontEnd` for ensembles).
 """
 from .features import (  # noqa: F401
     SpecParams, FbankParams, MfccParams, PRESETS,
@@ -11,6 +12,6 @@ from .features import (  # noqa: F401
     spec, fbank, mfcc, compute_spec, filter_banks, compute_mfcc,
     out_shape, bytes_per_clip, launch_count,
 )
-from .patch import patch_model  # noqa: F401
+from .patch import patch_model, SharedFrontEnd  # noqa: F401
 
 __version__ = "0.1"

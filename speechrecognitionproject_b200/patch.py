@@ -41,6 +41,55 @@ def detect_kind(module) -> str:
     raise TypeError("module has none of compute_mfcc / compute_spec / filter_banks")
 
 
+_FEATURE_SET = {"mfcc_bgru": "mfcc_tf", "mfrn_bgru": "mfcc_tf", "spec_bgru": "spec_tf", "spec_cnn": "spec_tf",
+                "fbanks_cnn": "fbank_tf"}
+
+
+class SharedFrontEnd:
+    """One PCM upload and one launch per feature set for an ENSEMBLE of patched models.
+
+    The reference's ensemble drivers feed the same ``batch['audio']`` to every member in turn
+    (analyst_training.py:91-94, predictions.py:59-60): each member recomputes its features on the CPU and
+    uploads them; ``spec_cnn`` and ``spec_bgru`` even compute the same spectrogram twice.  Members patched
+    with the same ``SharedFrontEnd`` share the device copy of the PCM batch and any feature set two of
+    them consume (both spectrogram models take the ``[B, 49, 321]`` tensor).
+
+    The cache holds exactly one batch.  A hit requires the *same tensor object* at the same
+    ``_version`` (in-place edits bump it); the object is kept referenced while cached, so its storage
+    cannot be recycled under the cache.  Cached features are shared read-only between the members
+    (none of the reference layers writes in place)."""
+
+    def __init__(self):
+        self._src = None
+        self._version = -1
+        self._dev = None
+        self._pcm = None
+        self._feat = {}
+        self.uploads = 0            # statistics (tests, logs)
+        self.launches = 0
+
+    def pcm(self, x: torch.Tensor, dev: torch.device) -> torch.Tensor:
+        if x is not self._src or x._version != self._version or dev != self._dev:
+            self._src, self._version, self._dev = x, x._version, dev
+            self._feat.clear()
+            if x.device != dev:
+                self._pcm = x.to(dev, non_blocking=True)
+                self.uploads += 1
+            else:
+                self._pcm = x
+        return self._pcm
+
+    def features(self, name: str, fn: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, dev: torch.device):
+        xd = self.pcm(x, dev)
+        if name not in self._feat:
+            self._feat[name] = fn(xd)
+            self.launches += 1
+        return self._feat[name]
+
+    def clear(self) -> None:
+        self.__init__()
+
+
 def default_feature_fn(kind: str) -> Callable[[torch.Tensor], torch.Tensor]:
     """Batched device features in the layout the model's first layer consumes."""
     if kind in ("mfcc_bgru", "mfrn_bgru"):
@@ -77,17 +126,21 @@ def _bgru_tail(self, x):
     return self.fc(x[:, -1, :])
 
 
-def make_forward(kind: str, feature_fn: Optional[Callable] = None):
+def make_forward(kind: str, feature_fn: Optional[Callable] = None, frontend: Optional[SharedFrontEnd] = None):
     if kind not in _KINDS:
         raise ValueError(f"unknown model kind {kind!r}; expected one of {_KINDS}")
     feat = feature_fn or default_feature_fn(kind)
 
     def forward(self, x):
         dev = next(self.parameters()).device
-        if x.device != dev:
-            x = x.to(dev, non_blocking=True)           # the only H2D: raw PCM
         with torch.no_grad():                          # features are never differentiated (:29)
-            f = feat(x)
+            if frontend is not None:                   # ensemble: upload / launch once per batch and feature set
+                f = frontend.features(_FEATURE_SET[kind], feat, x, dev)
+                x = frontend.pcm(x, dev)
+            else:
+                if x.device != dev:
+                    x = x.to(dev, non_blocking=True)   # the only H2D: raw PCM
+                f = feat(x)
         if f.device != dev:
             f = f.to(dev)
         if kind in ("mfcc_bgru", "spec_bgru"):
@@ -102,16 +155,18 @@ def make_forward(kind: str, feature_fn: Optional[Callable] = None):
     return forward
 
 
-def patch_model(module, kind: Optional[str] = None, feature_fn: Optional[Callable] = None) -> str:
+def patch_model(module, kind: Optional[str] = None, feature_fn: Optional[Callable] = None,
+                frontend: Optional[SharedFrontEnd] = None) -> str:
     """Patch ``module.Network.forward`` in place; returns the detected model kind.
 
     ``feature_fn(x[B,N]) -> features`` overrides the feature producer (tests use it to
-    check the re-plumbed ``forward`` against the reference's own on the CPU)."""
+    check the re-plumbed ``forward`` against the reference's own on the CPU).
+    ``frontend``: a ``SharedFrontEnd`` common to the members of an ensemble."""
     kind = kind or detect_kind(module)
     net = module.Network
     if not hasattr(net, "__srfe_original_forward__"):
         net.__srfe_original_forward__ = net.forward
-    net.forward = make_forward(kind, feature_fn)
+    net.forward = make_forward(kind, feature_fn, frontend)
     return kind
 
 

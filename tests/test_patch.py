@@ -161,3 +161,110 @@ def test_standin_gpu_real_kernels(srfe_lib, factory, kind):
         got_dev_pcm = net(x.cuda())                    # PCM already resident
     assert got_host_pcm.is_cuda and torch.equal(got_host_pcm, got_dev_pcm)
     torch.testing.assert_close(got_host_pcm.cpu(), want, rtol=2e-3, atol=2e-3)
+
+
+def _standin_spec(kind):
+    """spec_bgru / spec_cnn stand-ins (same attribute names and layer order as the reference modules)."""
+    m = types.ModuleType(f"standin_{kind}")
+
+    def compute_spec(sample):
+        y = oracle.spec_ref(sample.numpy())
+        return torch.from_numpy(np.ascontiguousarray(y.T if kind == "spec_cnn" else y))
+
+    if kind == "spec_bgru":
+        class Network(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.gru = nn.GRU(321, hidden_size=8, num_layers=1, bidirectional=True, batch_first=True)
+                self.fc = nn.Linear(16, 12)
+
+            def forward(self, x):
+                with torch.no_grad():
+                    inx = torch.ones(x.size(0), 321, 49)
+                    for i in range(x.size(0)):
+                        inx[i] = m.compute_spec(x[i])
+                inx = inx.to(next(self.parameters()).device).transpose(1, 2)
+                inx, _ = self.gru(inx)
+                return self.fc(inx[:, -1, :])
+    else:
+        class Network(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.conv1 = nn.Conv2d(1, 4, kernel_size=(7, 3), padding=(3, 1))
+                self.maxpool1 = nn.MaxPool2d((1, 3))
+                self.conv2 = nn.Conv2d(4, 4, (1, 7), padding=(0, 3))
+                self.maxpool2 = nn.MaxPool2d((1, 4))
+                self.conv3 = nn.Conv2d(4, 8, (1, 26))
+                self.conv4 = nn.Conv2d(8, 8, (7, 1), padding=(3, 0))
+                self.maxpool3 = nn.MaxPool1d(49)
+                self.dropout = nn.Dropout()
+                self.fc1 = nn.Linear(8, 8)
+                self.fc2 = nn.Linear(8, 12)
+
+            def forward(self, x):
+                with torch.no_grad():
+                    inx = torch.ones(x.size(0), 49, 321)
+                    for i in range(x.size(0)):
+                        inx[i] = m.compute_spec(x[i])
+                inx = inx.to(next(self.parameters()).device)
+                return patch._cnn_tail(self, inx)
+
+    m.compute_spec, m.Network = compute_spec, Network
+    return m
+
+
+def test_shared_front_end_dedups_ensemble_members():
+    """ensemble members patched with one SharedFrontEnd compute each feature set once per batch
+    (the two spectrogram models share theirs), recompute on a new batch and after an in-place edit."""
+    mods = {"spec_bgru": _standin_spec("spec_bgru"), "spec_cnn": _standin_spec("spec_cnn"),
+            "fbanks_cnn": _standin_fbanks_cnn()}
+    torch.manual_seed(3)
+    nets = {k: m.Network().eval() for k, m in mods.items()}
+    x = torch.from_numpy(oracle.synthetic_corpus(2, config_index=9))
+    with torch.no_grad():
+        want = {k: n(x) for k, n in nets.items()}
+    calls = []
+    fe = patch.SharedFrontEnd()
+    for k, m in mods.items():
+        fn = _oracle_fn(k)
+        patch.patch_model(m, kind=k, feature_fn=(lambda t, k=k, fn=fn: (calls.append(k), fn(t))[1]), frontend=fe)
+    with torch.no_grad():
+        got = {k: n(x) for k, n in nets.items()}
+    for k in mods:
+        torch.testing.assert_close(got[k], want[k], rtol=1e-5, atol=1e-5)
+    assert calls == ["spec_bgru", "fbanks_cnn"] and fe.launches == 2 and fe.uploads == 0     # spec_cnn reused spec_bgru's
+    with torch.no_grad():
+        nets["spec_cnn"](x)                                  # same batch again: still cached
+    assert fe.launches == 2
+    x[0, 0] += 1.0                                           # in-place edit bumps the version -> recompute
+    with torch.no_grad():
+        nets["spec_cnn"](x)
+    assert fe.launches == 3
+    y = x.clone()
+    with torch.no_grad():
+        nets["spec_bgru"](y)                                 # another batch object
+    assert fe.launches == 4
+    for m in mods.values():
+        patch.unpatch_model(m)
+
+
+@pytest.mark.gpu
+def test_shared_front_end_gpu(srfe_lib):
+    mods = {"spec_bgru": _standin_spec("spec_bgru"), "spec_cnn": _standin_spec("spec_cnn"),
+            "fbanks_cnn": _standin_fbanks_cnn(), "mfcc_bgru": _standin_mfcc_bgru()}
+    torch.manual_seed(4)
+    nets = {k: m.Network().eval() for k, m in mods.items()}
+    x = torch.from_numpy(oracle.synthetic_corpus(3, config_index=10))
+    with torch.no_grad():
+        want = {k: n(x) for k, n in nets.items()}          # reference-style CPU loops with oracle features
+    fe = patch.SharedFrontEnd()
+    for k, m in mods.items():
+        nets[k].cuda()
+        patch.patch_model(m, kind=k, frontend=fe)
+    with torch.no_grad():
+        got = {k: n(x) for k, n in nets.items()}
+    assert fe.uploads == 1 and fe.launches == 3             # one PCM H2D; spec, fbank, mfcc once each
+    for k in mods:
+        torch.testing.assert_close(got[k].cpu(), want[k], rtol=2e-3, atol=2e-3)
+    for m in mods.values():
+        patch.unpatch_model(m)
