@@ -7,7 +7,9 @@
 // plain C++ body on the host) -- so a wrong permutation or twiddle shows up in
 // `pytest -m "not gpu"` instead of costing a GPU round trip.  Not part of the product;
 // never used as a fallback.
+#include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../speechrecognitionproject_b200/csrc/srfe_fft.cuh"
@@ -86,4 +88,51 @@ extern "C" int emu_dft2(int n, const float* a_ri, const float* b_ri, float* oa_r
         ob_ri[2 * i] = v[i].re.hi; ob_ri[2 * i + 1] = v[i].im.hi;
     }
     return 0;
+}
+
+// ---- mel / filterbank projection through the kernels' ELL tables (srfe_tables.cpp: to_sparse, to_ell) ----------
+// Walks the tables exactly like the kernel's lane-per-filter loop (srfe_kernels.cuh: planar float2 weights, bank-skewed
+// starts, uniform group run length) on one power spectrum.  `power` holds n_bins values; whatever the padded runs read
+// beyond the filters' supports is filled with a large finite number, so a non-zero padding weight would show.
+// Returns the worst number of lanes of a 16-filter group that start in the same shared-memory bank pair.
+template <typename P>
+static int ell_project(const P& p, bool mfcc, const float* power, double* out, int* max_reach) {
+    std::vector<double> dense;
+    SparseBank sb;
+    EllBank ell;
+    const int n_bins = p.n_fft / 2 + 1;
+    int n_filt;
+    if constexpr (std::is_same<P, srfe_mfcc_params>::value) { mfcc_filters(p, dense); n_filt = p.n_mels; }
+    else { fbank_filters(p, dense); n_filt = p.nfilt; }
+    (void)mfcc;
+    to_sparse(dense, n_filt, n_bins, 1.0, sb);
+    to_ell(sb, ell);
+    std::vector<float> pbuf(std::max(ell.max_reach, n_bins) + 16, 1.0e30f);
+    for (int k = 0; k < n_bins; ++k) pbuf[k] = power[k];
+    int worst = 0;
+    for (int g = 0; g < ell.groups; ++g) {
+        const int off4 = ell.gmeta[2 * g], n4 = ell.gmeta[2 * g + 1];
+        int hits[16] = {0};
+        for (int l = 0; l < 16; ++l) {
+            const int m = 16 * g + l;
+            if (ell.start[m] < 0) return -1;
+            worst = std::max(worst, ++hits[ell.start[m] & 15]);
+            double acc = 0.0;
+            for (int q4 = 0; q4 < n4; ++q4)
+                for (int j = 0; j < 4; ++j) {
+                    const float w = ell.w4[((((size_t)(off4 + q4) * 2 + (j >> 1)) * 16 + l) * 2) + (j & 1)];
+                    if (w != 0.f) acc += (double)w * (double)pbuf[ell.start[m] + 4 * q4 + j];     // 0 * 1e30 stays 0 on the device too
+                    else if (!(pbuf[ell.start[m] + 4 * q4 + j] == pbuf[ell.start[m] + 4 * q4 + j])) return -2;
+                }
+            if (m < n_filt) out[m] = acc;
+        }
+    }
+    *max_reach = ell.max_reach;
+    return worst;
+}
+extern "C" int emu_ell_project_mfcc(const srfe_mfcc_params* p, const float* power, double* out, int* max_reach) {
+    return ell_project(*p, true, power, out, max_reach);
+}
+extern "C" int emu_ell_project_fbank(const srfe_fbank_params* p, const float* power, double* out, int* max_reach) {
+    return ell_project(*p, false, power, out, max_reach);
 }

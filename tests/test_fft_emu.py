@@ -44,3 +44,38 @@ def test_real_fft_power_pairs(emu_lib, nfft):
         for x, p in ((xa, pa), (xb, pb)):
             ref = np.abs(np.fft.rfft(x.astype(np.float64))) ** 2
             assert np.abs(p - ref).max() <= 2e-6 * max(ref.max(), 1e-30)
+
+
+@pytest.mark.parametrize("name", ["R-FBANK", "C-FBANK", "R-MFCC", "C-MFCC", "generic-fbank-26", "generic-mfcc-80"])
+def test_ell_filterbank_tables(emu_lib, name):
+    """Host table logic of the mel / filterbank stage (srfe_tables.cpp: to_sparse -> to_ell): walking the planar,
+    bank-skewed ELL tables the way the kernel does reproduces the dense matrix product, padded reads carry zero weights,
+    the runs stay inside the per-half-warp power buffer, and at most two of the 16 filters of a group start in the same
+    bank pair for the presets (the skew's purpose; unskewed banks have 4- to 8-way groups)."""
+    import ctypes as C
+    import speechrecognitionproject_b200 as S
+    from speechrecognitionproject_b200 import _lib
+    presets = {"R-FBANK": S.R_FBANK, "C-FBANK": S.C_FBANK, "R-MFCC": S.R_MFCC, "C-MFCC": S.C_MFCC,
+               "generic-fbank-26": S.FbankParams(nfilt=26), "generic-mfcc-80": S.MfccParams(n_fft=512, win_length=400, hop=160, n_mels=80, n_mfcc=13)}
+    p = presets[name]
+    is_mfcc = isinstance(p, S.MfccParams)
+    lib = _lib.lib()
+    n_fft = p.n_fft if is_mfcc else p.nfft
+    n_bins, n_filt = n_fft // 2 + 1, (p.n_mels if is_mfcc else p.nfilt)
+    dense = np.zeros((n_filt, n_bins))
+    pc = p.to_c()
+    fn = lib.srfe_mfcc_filters_f64 if is_mfcc else lib.srfe_fbank_filters_f64
+    assert fn(C.byref(pc), dense.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    rng = np.random.default_rng(7)
+    power = (rng.random(n_bins) * 1e6).astype(np.float32)
+    out = np.zeros(n_filt)
+    reach = C.c_int(0)
+    emu = emu_lib.emu_ell_project_mfcc if is_mfcc else emu_lib.emu_ell_project_fbank
+    emu.restype = C.c_int
+    worst = emu(C.byref(pc), power.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(reach))
+    assert worst >= 1, f"emulator error {worst}"
+    want = dense @ power.astype(np.float64)
+    np.testing.assert_allclose(out, want, rtol=2e-6, atol=1e-3)          # weights are stored as float32
+    assert reach.value <= (272 if n_fft == 512 else 400)                 # FftGeom<N>::SCRATCH_P2 slots
+    if not name.startswith("generic"):
+        assert worst <= 2, f"{name}: {worst} filters of a group share a bank pair"
