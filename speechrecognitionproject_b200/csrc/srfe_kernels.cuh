@@ -322,6 +322,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             for (int i = tid; i < p.dct_bytes / 16; i += nthr) vd[i] = __ldg(vs + i);
         }
     }
+    {   // The padded mel runs read (with zero weights) a few power-buffer slots that neither the exchange nor the power
+        // store ever writes: give them a finite value once, 0 x stale NaN bits would poison a band sum.
+        int4* z = reinterpret_cast<int4*>(smem + p.sm_scratch);
+        for (int i = tid; i < (p.sm_tile - p.sm_scratch) / 16; i += nthr) z[i] = make_int4(0, 0, 0, 0);
+    }
     const float* s_win = reinterpret_cast<const float*>(smem + p.off_win);
     FftTables T;
     T.tw1 = reinterpret_cast<const cpx*>(smem + p.off_tw1);
