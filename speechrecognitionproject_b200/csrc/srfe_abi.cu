@@ -212,21 +212,26 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.dct_row0_sum = (float)rs0;                                   // = sqrt(n_mels)
     // Folded DCT tables (n_mels % 4 == 0).  The DCT-II symmetry D[k][n-1-f] = (-1)^k D[k][f] lets even k work on
     // s[f] = x[f] + x[n-1-f] and odd k on d[f] = x[f] - x[n-1-f], f < n/2.  One kernel thread owns one frame pair and
-    // one block of CB same-parity coefficients; the table of a block is [f < n/2][RW] floats (RW = 4 or 8, zero
-    // padded) so a thread reads its coefficients for one f with one or two LDS.128.  Which CB fills the CTA best
-    // depends on the frame count and the launch shape, so every CB gets its own copy after the common tables.
+    // one block of CB same-parity coefficients; a block's table is a float4 plane [f < n/2] (coefficients 0..3) plus,
+    // for CB > 4, a second plane of 1 / 2 / 4 floats per f: one LDS.128 and at most one more load per f.  Which CB
+    // fills the CTA best depends on the frame count and the launch shape, so every CB gets its own copy after the
+    // common tables.
     e->kp.dct_fold = (p.n_mels >= 4 && p.n_mels % 4 == 0) ? 1 : 0;
     e->blob_common = (int)bb.data.size();
     if (e->kp.dct_fold) {
         const int half = p.n_mels / 2, ne = (p.n_mfcc + 1) / 2, no = p.n_mfcc / 2;
         for (int cb : {2, 3, 4, 5, 6, 8}) {
-            const int rw = cb <= 4 ? 4 : 8;
+            const int rb = cb <= 4 ? 0 : cb == 5 ? 1 : cb == 6 ? 2 : 4;       // floats per entry in the second plane
             Entry::DctVar v{cb, (ne + cb - 1) / cb, (no + cb - 1) / cb, 0, 0};
-            std::vector<float> tab((size_t)(v.nbe + v.nbo) * half * rw, 0.f);
+            const size_t nent = (size_t)(v.nbe + v.nbo) * half;
+            std::vector<float> tab(((nent * (4 + rb) + 3) / 4) * 4, 0.f);
             for (int k = 0; k < p.n_mfcc; ++k) {
-                const int j = k >> 1, blk = (k & 1) * v.nbe + j / cb;
-                for (int f = 0; f < half; ++f)
-                    tab[((size_t)blk * half + f) * rw + j % cb] = (float)dct[(size_t)k * p.n_mels + f];
+                const int j = k >> 1, blk = (k & 1) * v.nbe + j / cb, jj = j % cb;
+                for (int f = 0; f < half; ++f) {
+                    const size_t ent = (size_t)blk * half + f;
+                    const float d = (float)dct[(size_t)k * p.n_mels + f];
+                    if (jj < 4) tab[ent * 4 + jj] = d; else tab[nent * 4 + ent * rb + (jj - 4)] = d;
+                }
             }
             v.bytes = (int)tab.size() * 4;
             v.off = bb.add(tab.data(), tab.size() * 4);

@@ -231,7 +231,8 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 //   work item = (block of CB same-parity coefficients, PQ frame pairs); one THREAD per item, items dealt over the
 //   whole CTA, nothing is combined across lanes.  Per f the thread reads its pairs' folded values (PQ LDS.64) and its
 //   block's CB coefficients (LDS.128 [+ LDS], the same address for all lanes of a block) and issues PQ CB FFMA2.
-//   Table layout: [block][f < n/2][RW] floats, RW = 4 (CB <= 4) or 8, even-k blocks first.
+//   Table layout: a float4 plane [block][f < n/2] with coefficients 0..3 of the block, then a plane of 1 / 2 / 4 floats
+//   per entry with coefficients 4.. (CB > 4); even-k blocks first.
 //   The phase is bound by shared-memory wavefronts or by FFMA2 issue depending on the tile; the host picks (CB, PQ)
 //   from a small cost model (srfe_abi.cu: smem_plan).
 //   Measured alternatives, all slower: warp tasks of 4 coefficients x 64 pairs with the f range split over half-warps
@@ -241,7 +242,7 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 template <int CB, int PQ>
 __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, const float* dtab, const P2* fmeanP,
                                           float* ctile, float thr, int npairs, int TC, int tid, int nthr) {
-    constexpr int RW = CB <= 4 ? 4 : 8;
+    constexpr int RB = CB <= 4 ? 0 : CB == 5 ? 1 : CB == 6 ? 2 : 4;    // floats per entry in the second plane
     const int half = p.n_filt >> 1, TSP = p.tile_stride;
     const int nq = (npairs + PQ - 1) / PQ;                              // a thread's pairs: q, q + nq, ... (row stride TSP
     const int nqp = (nq + 15) & ~15;                                    //  between lanes keeps the LDS.64 conflict-free);
@@ -253,7 +254,8 @@ __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, con
         const P2* x[PQ];
 #pragma unroll
         for (int i = 0; i < PQ; ++i) x[i] = tileP + min(q0 + i * nq, npairs - 1) * TSP + par * half;   // s[0..half) | d[0..half)
-        const float4* d = reinterpret_cast<const float4*>(dtab) + b * half * (RW / 4);
+        const float4* d = reinterpret_cast<const float4*>(dtab) + b * half;
+        const float* e = dtab + 4 * (p.dct_nbe + p.dct_nbo) * half + RB * b * half;
         P2 acc[PQ][CB];
 #pragma unroll
         for (int i = 0; i < PQ; ++i)
@@ -262,9 +264,11 @@ __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, con
 #pragma unroll 4
         for (int f = 0; f < half; ++f) {
             float c[8];
-            const float4 d0 = d[f * (RW / 4)];
+            const float4 d0 = d[f];
             c[0] = d0.x; c[1] = d0.y; c[2] = d0.z; c[3] = d0.w;
-            if (RW == 8) { const float4 d1 = d[f * 2 + 1]; c[4] = d1.x; c[5] = d1.y; c[6] = d1.z; c[7] = d1.w; }
+            if (RB == 1) c[4] = e[f];
+            if (RB == 2) { const float2 d1 = *reinterpret_cast<const float2*>(e + 2 * f); c[4] = d1.x; c[5] = d1.y; }
+            if (RB == 4) { const float4 d1 = *reinterpret_cast<const float4*>(e + 4 * f); c[4] = d1.x; c[5] = d1.y; c[6] = d1.z; c[7] = d1.w; }
 #pragma unroll
             for (int i = 0; i < PQ; ++i) {
                 const P2 xv = x[i][f];
@@ -360,8 +364,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             P2 pa[G::M / 32], pb[G::M / 32], pmid;
             const bool active = (it * HW + (hw & ~1)) < npairs;
             if (active) {                                   // warp-uniform: both half-warps of a warp run together
-                // (holding the NEXT pair in registers while this one is transformed was measured: it spills at
-                //  128 registers and gains nothing at 168 / 12 warps; prefetch.global.L1 has no effect either)
+                // (holding the NEXT pair in registers was measured three ways -- fetched before the output stage, fetched
+                //  after the power values went to shared memory so that the loads fly under the mel loop, and at 168
+                //  registers / 12 warps: it spills or gains nothing; prefetch.global.L1 has no effect either.  The stall on
+                //  the first use of the samples stays at ~6 % of warp time.)
                 RawFrame<FAM, NJ> rawA, rawB;
                 const FramePos cA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc), cB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
                 fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cA.c) * p.clip_stride, p.start0 + cA.t * p.hop, l, rawA);
