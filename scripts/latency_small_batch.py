@@ -1,0 +1,21 @@
+"""Per-call latency at the reference's own batch sizes (ensemble drivers use batch_size=1). Dev tool."""
+import sys, time, json, torch
+sys.path.insert(0, ".")
+import speechrecognitionproject_b200 as S
+for name in ("R-MFCC", "R-SPEC", "R-FBANK", "C-MFCC"):
+    p = S.PRESETS[name]
+    fn = {"SpecParams": S.spec, "FbankParams": S.fbank, "MfccParams": S.mfcc}[type(p).__name__]
+    for B in (1, 8, 64, 512):
+        x = (torch.randn(B, 16000, device="cuda") * 3000).round()
+        for _ in range(20): fn(x, p)
+        torch.cuda.synchronize()
+        n = 300
+        t0 = time.perf_counter()
+        for _ in range(n): y = fn(x, p)
+        t_issue = (time.perf_counter() - t0) / n          # host time to issue (async)
+        torch.cuda.synchronize()
+        t_all = (time.perf_counter() - t0) / n
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); y = fn(x, p); b.record(); torch.cuda.synchronize()
+        print(json.dumps({"preset": name, "B": B, "host_issue_us": round(t_issue * 1e6, 1), "per_call_us": round(t_all * 1e6, 1),
+                          "kernel_us": round(a.elapsed_time(b) * 1e3, 1)}))

@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -356,7 +357,8 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
             const int smem = smem_plan(e, kp, warps, budget, &pl);
             if (smem < 0 || smem > budget) continue;
             for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
-                if (cpc > 1 && cpc > kp.n_clips) break;
+                // small batches: never trade CTAs for clips per group (8 clips as one group would run on one SM)
+                if (cpc > 1 && (kp.n_clips + cpc - 1) / cpc < 2 * di.sms) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
                 // Fitted to scripts/tune.py sweeps on the B200 (profiles/r1_notes.md): throughput ~ round efficiency x
@@ -391,6 +393,14 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
     return SRFE_OK;
 }
 
+struct ConfigKey {
+    const Entry* e; int T, n_clips, layout; const DevInfo* di;
+    bool operator<(const ConfigKey& o) const {
+        return std::tie(e, T, n_clips, layout, di) < std::tie(o.e, o.T, o.n_clips, o.layout, o.di);
+    }
+};
+static std::map<ConfigKey, Config> g_configs;                       // guarded by g_mu
+
 static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     if (e->family == FAM_MFCC && kp.n_deltas > 0 && kp.T < 2) return fail(SRFE_ERR_UNSUPPORTED, "mfcc: deltas need at least 2 frames");
     if (kp.n_clips == 0 || kp.T == 0) return SRFE_OK;
@@ -398,8 +408,24 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     int rc = dev_info(&di);
     if (rc != SRFE_OK) return rc;
     Config cfg;
-    rc = pick_config(e, kp, *di, &cfg);
-    if (rc != SRFE_OK) return rc;
+    {   // the choice depends on (parameter set, frames per clip, batch size up to the point where the grid is full):
+        // remember it -- small-batch callers (the reference's ensemble drivers run batch_size = 1) pay for the search once
+        static const char* const kOverrides[] = {"SRFE_WARPS", "SRFE_CTAS", "SRFE_CPC", "SRFE_DCT_CB", "SRFE_DCT_PQ"};
+        bool overridden = false;
+        for (const char* k : kOverrides) { const char* v = getenv(k); overridden = overridden || (v && *v); }
+        const ConfigKey key{e, kp.T, std::min(kp.n_clips, 16 * di->sms), kp.layout, di};   // beyond that every cpc is allowed
+        bool hit = false;
+        if (!overridden) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            auto it = g_configs.find(key);
+            if (it != g_configs.end()) { cfg = it->second; hit = true; }
+        }
+        if (!hit) {
+            rc = pick_config(e, kp, *di, &cfg);
+            if (rc != SRFE_OK) return rc;
+            if (!overridden) { std::lock_guard<std::mutex> lk(g_mu); g_configs[key] = cfg; }
+        }
+    }
     kp.cpc = cfg.cpc;
     kp.n_groups = (kp.n_clips + cfg.cpc - 1) / cfg.cpc;
     kp.sm_scratch = cfg.blob;

@@ -19,6 +19,7 @@ like the reference's return values.  There is no CPU implementation here.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass, replace
 from typing import Optional
 
@@ -148,10 +149,34 @@ def _suffix(x: torch.Tensor) -> str:
 
 def _run_device(fam: str, cp, x: torch.Tensor, out: torch.Tensor) -> None:
     fn = getattr(_lib.lib(), f"srfe_{fam}_{_suffix(x)}")
+    stride = x.stride(0) if x.size(0) > 1 else x.size(1)
+    if x.device.index == torch.cuda.current_device():          # the common case: skip the device-guard round trip
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(fn(x.data_ptr(), x.size(0), x.size(1), stride, C.byref(cp), out.data_ptr(), stream))
+        return
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        stride = x.stride(0) if x.size(0) > 1 else x.size(1)
         _lib.check(fn(x.data_ptr(), x.size(0), x.size(1), stride, C.byref(cp), out.data_ptr(), stream))
+
+
+# Eager fast path.  The reference's ensemble drivers call the models with batch_size = 1
+# (analyst_training.py:84, predictions.py:58): per-call host overhead is what such callers see.  Outside of
+# torch.compile tracing the public functions therefore call the kernels directly (same code as the registered
+# ops below, minus the dispatcher); parameter structs and output shapes are cached per (frozen) parameter set.
+@functools.lru_cache(maxsize=256)
+def _c_params(params):
+    return params.to_c()
+
+
+@functools.lru_cache(maxsize=4096)
+def _cached_shape(params, n_samples: int) -> tuple[int, int]:
+    return out_shape(params, n_samples)
+
+
+def _eager_device(fam: str, params, xb: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((xb.size(0),) + _cached_shape(params, xb.size(1)), dtype=torch.float32, device=xb.device)
+    _run_device(fam, _c_params(params), xb, out)
+    return out
 
 
 @torch.library.custom_op("srfe::spec", mutates_args=(), device_types="cuda")
@@ -224,7 +249,9 @@ def _run_host(fam: str, cp, x: torch.Tensor, shape: tuple[int, int], device: Opt
 def _dispatch(fam: str, params, x: torch.Tensor, device: Optional[int]) -> torch.Tensor:
     single = x.dim() == 1
     xb = _prep(x.unsqueeze(0) if single else x)
-    if xb.is_cuda:
+    if xb.is_cuda and not torch.compiler.is_compiling():
+        y = _eager_device(fam, params, xb)
+    elif xb.is_cuda:
         c = params.to_c()
         if fam == "spec":
             y = torch.ops.srfe.spec(xb, c.sample_rate, c.nperseg, c.noverlap, bool(c.take_log), c.log_eps, c.layout)
@@ -241,7 +268,7 @@ def _dispatch(fam: str, params, x: torch.Tensor, device: Optional[int]) -> torch
 def spec(x: torch.Tensor, params: SpecParams = R_SPEC, *, layout: Optional[str] = None,
          device: Optional[int] = None) -> torch.Tensor:
     """Batched ``compute_spec``: ``x[B, N]`` -> ``[B, nperseg/2+1, T]`` ('ft') or ``[B, T, nperseg/2+1]`` ('tf')."""
-    if layout is not None:
+    if layout is not None and layout != params.layout:
         params = replace(params, layout=layout)
     return _dispatch("spec", params, x, device)
 
@@ -254,7 +281,7 @@ def fbank(x: torch.Tensor, params: FbankParams = R_FBANK, *, device: Optional[in
 def mfcc(x: torch.Tensor, params: MfccParams = R_MFCC, *, layout: Optional[str] = None,
          device: Optional[int] = None) -> torch.Tensor:
     """Batched ``compute_mfcc``: ``x[B, N]`` -> ``[B, (1+n_deltas) n_mfcc, T]`` ('ft') or transposed ('tf')."""
-    if layout is not None:
+    if layout is not None and layout != params.layout:
         params = replace(params, layout=layout)
     return _dispatch("mfcc", params, x, device)
 
