@@ -420,3 +420,21 @@ def test_thread_safety_two_host_threads(srfe_lib, corpus):
     for t in hs: t.join()
     ref = S.mfcc(x, S.R_MFCC).cpu()
     assert all(torch.equal(res[i], ref) for i in range(3))
+
+
+def test_one_process_two_devices(srfe_lib, corpus):
+    """one process driving several GPUs is legal -- tables are cached per device and the launch goes to the
+    device that owns the tensor, whatever the current device is.  Skipped on single-GPU boxes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    x0 = torch.from_numpy(corpus).to("cuda:0")
+    x1 = x0.to("cuda:1")
+    for fn, p in ((S.mfcc, S.R_MFCC), (S.spec, S.R_SPEC), (S.fbank, S.R_FBANK)):
+        y0 = fn(x0, p)
+        with torch.cuda.device(0):
+            y1 = fn(x1, p)                      # current device 0, data on device 1
+        assert y1.device == x1.device
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        assert torch.equal(y0.cpu(), y1.cpu())
+    xc = torch.from_numpy(corpus)
+    assert torch.equal(S.mfcc(xc, S.R_MFCC, device=1), S.mfcc(xc, S.R_MFCC, device=0))      # host entry points, per device
