@@ -438,3 +438,43 @@ def test_one_process_two_devices(srfe_lib, corpus):
         assert torch.equal(y0.cpu(), y1.cpu())
     xc = torch.from_numpy(corpus)
     assert torch.equal(S.mfcc(xc, S.R_MFCC, device=1), S.mfcc(xc, S.R_MFCC, device=0))      # host entry points, per device
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_parameter_sets_and_lengths(srfe_lib, seed):
+    """Random feature parameters, clip lengths and batch sizes against the float64 oracle: walks launch shapes, window
+    extents, filterbank shapes and DCT tile choices the presets never reach (scripts/fuzz_shapes.py runs more)."""
+    rng = np.random.default_rng(seed)
+    done = 0
+    for case in range(30):
+        n_fft = int(rng.choice([512, 640]))
+        n_samples = int(rng.choice([4000, 8000, 16000, 24000, 12346]))
+        x = oracle.synthetic_corpus(int(rng.choice([1, 3])), config_index=30 + case % 5, n_samples=n_samples)
+        xd = torch.from_numpy(x).cuda()
+        fam = rng.choice(["mfcc", "mfcc", "fbank", "spec"])
+        try:
+            if fam == "mfcc":
+                n_mels = int(rng.choice([20, 26, 40, 64, 80, 128, 200]))
+                p = S.MfccParams(n_fft=n_fft, win_length=int(rng.choice([n_fft, 400, 320, 256])),
+                                 hop=int(rng.choice([80, 128, 160, 200, 320])), n_mels=n_mels,
+                                 n_mfcc=int(rng.integers(1, min(64, n_mels) + 1)), n_deltas=int(rng.integers(0, 3)),
+                                 layout=str(rng.choice(["ft", "tf"])))
+                got = S.mfcc(xd, p).cpu().numpy()
+                truth = H.oracle_batch(oracle.mfcc_truth, x, H.to_oracle_params(p))
+                if p.layout == "tf":
+                    truth = truth.transpose(0, 2, 1)                  # the oracle is always [coeff, time]
+                H.check_mfcc(got, truth, str(p))
+            elif fam == "fbank":
+                p = S.FbankParams(nfft=n_fft, frame_len=int(rng.choice([400, 320, 512])), frame_step=int(rng.choice([80, 160, 200])),
+                                  nfilt=int(rng.choice([13, 26, 40, 64, 120])))
+                got = S.fbank(xd, p).cpu().numpy()
+                H.check_logmel(got, H.oracle_batch(oracle.fbank_truth, x, H.to_oracle_params(p)), str(p))
+            else:
+                p = S.SpecParams(nperseg=n_fft, noverlap=int(rng.choice([n_fft // 2, n_fft // 4, n_fft - 160, 0])), log=False,
+                                 layout=str(rng.choice(["ft", "tf"])))
+                got = S.spec(xd, p).cpu().numpy()
+                H.check_psd(got, H.oracle_batch(oracle.spec_truth, x, H.to_oracle_params(p)), str(p))
+            done += 1
+        except RuntimeError as e:                                     # shapes the kernels decline are declined loudly
+            assert "SRFE_ERR_TOO_LARGE" in str(e) or "SRFE_ERR_UNSUPPORTED" in str(e) or "SRFE_ERR_BAD_ARG" in str(e), str(e)
+    assert done >= 20
