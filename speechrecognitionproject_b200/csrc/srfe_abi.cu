@@ -423,7 +423,11 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
         if (!hit) {
             rc = pick_config(e, kp, *di, &cfg);
             if (rc != SRFE_OK) return rc;
-            if (!overridden) { std::lock_guard<std::mutex> lk(g_mu); g_configs[key] = cfg; }
+            if (!overridden) {
+                std::lock_guard<std::mutex> lk(g_mu);
+                if (g_configs.size() >= 4096) g_configs.clear();    // variable-length callers: bounded memory
+                g_configs[key] = cfg;
+            }
         }
     }
     kp.cpc = cfg.cpc;
