@@ -19,3 +19,22 @@ for name in ("R-MFCC", "R-SPEC", "R-FBANK", "C-MFCC"):
         a.record(); y = fn(x, p); b.record(); torch.cuda.synchronize()
         print(json.dumps({"preset": name, "B": B, "host_issue_us": round(t_issue * 1e6, 1), "per_call_us": round(t_all * 1e6, 1),
                           "kernel_us": round(a.elapsed_time(b) * 1e3, 1)}))
+
+# the same call captured in a CUDA graph (three front ends of an ensemble step, batch 1)
+x = (torch.randn(1, 16000, device="cuda") * 3000).round()
+fns = lambda: (S.mfcc(x, S.R_MFCC, layout="tf"), S.fbank(x, S.R_FBANK), S.spec(x, S.R_SPEC, layout="tf"))
+fns(); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    outs = fns()
+for _ in range(20): g.replay()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(300): g.replay()
+torch.cuda.synchronize()
+t_graph = (time.perf_counter() - t0) / 300
+t0 = time.perf_counter()
+for _ in range(300): fns()
+torch.cuda.synchronize()
+t_eager = (time.perf_counter() - t0) / 300
+print(json.dumps({"ensemble_step_B1_three_front_ends": {"eager_us": round(t_eager * 1e6, 1), "cuda_graph_us": round(t_graph * 1e6, 1)}}))

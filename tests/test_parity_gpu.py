@@ -478,3 +478,24 @@ def test_random_parameter_sets_and_lengths(srfe_lib, seed):
         except RuntimeError as e:                                     # shapes the kernels decline are declined loudly
             assert "SRFE_ERR_TOO_LARGE" in str(e) or "SRFE_ERR_UNSUPPORTED" in str(e) or "SRFE_ERR_BAD_ARG" in str(e), str(e)
     assert done >= 20
+
+
+def test_cuda_graph_capture_and_replay(srfe_lib, corpus):
+    """The device entry points are plain stream-ordered launches (no allocation, no synchronisation once the tables of
+    a parameter set exist): they can be captured into a CUDA graph and replayed on new data."""
+    x = torch.from_numpy(corpus).cuda()
+    static_in = x.clone()
+    want = [S.mfcc(x, S.R_MFCC, layout="tf"), S.fbank(x, S.R_FBANK), S.spec(x, S.R_SPEC)]       # warm-up: tables, attributes
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = [S.mfcc(static_in, S.R_MFCC, layout="tf"), S.fbank(static_in, S.R_FBANK), S.spec(static_in, S.R_SPEC)]
+    g.replay()
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
+    static_in.copy_(x.flip(0))                          # new data, same graph
+    g.replay()
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w.flip(0))
