@@ -173,6 +173,13 @@ int64_t srfe_spec_bytes_per_clip (const srfe_spec_params*  p, int64_t n_samples)
 int64_t srfe_fbank_bytes_per_clip(const srfe_fbank_params* p, int64_t n_samples);
 int64_t srfe_mfcc_bytes_per_clip (const srfe_mfcc_params*  p, int64_t n_samples);
 
+/* device (global-memory) workspace the device entry points need for this call: always 0 -- PCM to features runs in
+ * registers and shared memory; returns a negative srfe_status for invalid parameters.  (Host entry points keep a
+ * per-thread pinned staging + device buffer of their own.) */
+int64_t srfe_spec_workspace_bytes (const srfe_spec_params*  p, int64_t n_clips, int64_t n_samples);
+int64_t srfe_fbank_workspace_bytes(const srfe_fbank_params* p, int64_t n_clips, int64_t n_samples);
+int64_t srfe_mfcc_workspace_bytes (const srfe_mfcc_params*  p, int64_t n_clips, int64_t n_samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,9 @@ SYMBOLS = {
     "srfe_spec_bytes_per_clip": (_i64, [C.POINTER(SpecParamsC), _i64]),
     "srfe_fbank_bytes_per_clip": (_i64, [C.POINTER(FbankParamsC), _i64]),
     "srfe_mfcc_bytes_per_clip": (_i64, [C.POINTER(MfccParamsC), _i64]),
+    "srfe_spec_workspace_bytes": (_i64, [C.POINTER(SpecParamsC), _i64, _i64]),
+    "srfe_fbank_workspace_bytes": (_i64, [C.POINTER(FbankParamsC), _i64, _i64]),
+    "srfe_mfcc_workspace_bytes": (_i64, [C.POINTER(MfccParamsC), _i64, _i64]),
     "srfe_spec_window_f64": (_i32, [C.POINTER(SpecParamsC), _dp]),
     "srfe_fbank_window_f64": (_i32, [C.POINTER(FbankParamsC), _dp]),
     "srfe_mfcc_window_f64": (_i32, [C.POINTER(MfccParamsC), _dp]),

@@ -631,6 +631,21 @@ int64_t srfe_mfcc_bytes_per_clip(const srfe_mfcc_params* p, int64_t n) {
     return T < 0 ? T : n * 4 + s[0] * s[1] * 4;
 }
 
+// The device entry points need no global-memory workspace (everything between PCM and features lives in registers and
+// shared memory): the query exists so that a caller written against "caller owns output and workspace" has its answer.
+int64_t srfe_spec_workspace_bytes(const srfe_spec_params* p, int64_t n_clips, int64_t n) {
+    const int64_t T = srfe_spec_out_shape(p, n, nullptr);
+    return T < 0 ? T : (n_clips < 0 ? (int64_t)fail(SRFE_ERR_BAD_ARG, "n_clips < 0") : 0);
+}
+int64_t srfe_fbank_workspace_bytes(const srfe_fbank_params* p, int64_t n_clips, int64_t n) {
+    const int64_t T = srfe_fbank_out_shape(p, n, nullptr);
+    return T < 0 ? T : (n_clips < 0 ? (int64_t)fail(SRFE_ERR_BAD_ARG, "n_clips < 0") : 0);
+}
+int64_t srfe_mfcc_workspace_bytes(const srfe_mfcc_params* p, int64_t n_clips, int64_t n) {
+    const int64_t T = srfe_mfcc_out_shape(p, n, nullptr);
+    return T < 0 ? T : (n_clips < 0 ? (int64_t)fail(SRFE_ERR_BAD_ARG, "n_clips < 0") : 0);
+}
+
 static int copy_out(const std::vector<double>& v, double* dst) {
     if (!dst) return fail(SRFE_ERR_BAD_ARG, "output pointer is NULL");
     std::memcpy(dst, v.data(), v.size() * sizeof(double));

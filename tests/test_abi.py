@@ -49,6 +49,18 @@ def test_out_shapes_and_bytes(srfe_lib):
         assert S.out_shape(S.R_MFCC, n)[1] == oracle.mfcc_num_frames(n)
 
 
+def test_workspace_query(srfe_lib):
+    """The device entry points need no global workspace; the query validates its parameters like the others."""
+    import ctypes as C
+    import speechrecognitionproject_b200 as S
+    for fam, p in (("spec", S.R_SPEC), ("fbank", S.R_FBANK), ("mfcc", S.C_MFCC)):
+        fn = getattr(srfe_lib, f"srfe_{fam}_workspace_bytes")
+        assert fn(C.byref(p.to_c()), 262144, 16000) == 0
+        assert fn(C.byref(p.to_c()), -1, 16000) < 0
+    bad = S.MfccParams(n_fft=500).to_c()
+    assert srfe_lib.srfe_mfcc_workspace_bytes(C.byref(bad), 1, 16000) < 0
+
+
 def test_validation_errors(srfe_lib):
     bad = [S.SpecParams(nperseg=600, noverlap=300), S.SpecParams(noverlap=640), S.SpecParams(noverlap=319),
            S.FbankParams(frame_len=700), S.FbankParams(nfilt=0), S.FbankParams(frame_step=161),
