@@ -609,9 +609,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3.
             //
             // The contraction runs on the FP32 pipe in packed FFMA2 (both frames of a pair at once), NOT on tensor
-            // cores: measured on B200, the legacy mma.sync TF32 path retires ~1 HMMA.1688 per 21 cycles per SMSP, i.e.
-            // ~65 fp32-grade MAC/clk/SM after the 3xTF32 split fp32 accuracy needs, against 128 MAC/clk/SM for FFMA2
-            // (profiles/r1_notes.md), and tcgen05 would need split operand tiles that do not fit beside the dB tile.
+            // cores: measured on B200 (scripts/ubench/mma_overlap.cu), the legacy mma.sync TF32 path retires one
+            // HMMA.1688 per ~16 cycles per SMSP, i.e. ~65 fp32-grade MAC/clk/SM after the 3xTF32 split fp32 accuracy
+            // needs, against 128 MAC/clk/SM for FFMA2.  It is a pipe of its own, and a version of this contraction on
+            // it (overlapping the co-resident CTA's FFT) was built and measured at parity: no gain
+            // (profiles/r1_notes.md).  tcgen05 would need split operand tiles that do not fit beside the dB tile.
             // The DCT-II symmetry D[k][n-1-f] = (-1)^k D[k][f] halves the MACs: even k see s = x[f] + x[n-1-f],
             // odd k see d = x[f] - x[n-1-f], f < n/2.
             const int TC = (p.layout == SRFE_LAYOUT_FT) ? p.T : p.T + 1 + (p.T & 1);
