@@ -510,7 +510,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             const float da = 3.010299956639812f * lg2_ftz(fmaxf(acc.lo, p.amin));   // 10 log10
                             const float db = 3.010299956639812f * lg2_ftz(fmaxf(acc.hi, p.amin));
                             prow[m] = mkp(da, db);              // one STS.64 per filter and frame pair
-                            run_max = fmaxf(run_max, fmaxf(cA.ok ? da : -CUDART_INF_F, cB.ok ? db : -CUDART_INF_F));
+                            // (frames past the end alias the clip's last valid frame -- frame_pos -- so their values are
+                            //  values the maximum has seen anyway: no masking needed)
+                            run_max = fmaxf(run_max, fmaxf(da, db));
                             fsum = padd(fsum, mkp(da, db));
                         }
                     };
