@@ -324,8 +324,8 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
     }
     c->blob = blob;
     int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
-    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT)        // CTA-wide [bin][2 hw + 1] transposition tile
-        scratch = std::max(scratch, align16(e->n_bins * (2 * hw + 1) * 4));
+    if (e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT)        // CTA-wide [bin][2 hw + 2] transposition tile
+        scratch = std::max(scratch, align16(e->n_bins * (2 * hw + 2) * 4));
     int tile = 0;
     c->ctile_off = blob;
     if (e->family == FAM_MFCC) {

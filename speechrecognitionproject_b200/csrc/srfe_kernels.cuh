@@ -570,17 +570,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 // CTA-wide tile [bin][2 HW frames] aliased onto the (now idle) FFT scratch; rows of up to
                 // 2 HW consecutive frames leave as long runs along time
                 float* ft = reinterpret_cast<float*>(scratch_all);
-                const int RS = 2 * HW + 1;
+                const int RS = 2 * HW + 2;                  // even: the (A, B) pair of a bin goes out as one STS.64; 2 k (mod 32)
+                                                            // puts the 16 bins of a half-warp on 16 distinct bank pairs
                 __syncthreads();                            // every half-warp is done with its Z buffer
                 if (active) {
                     float* col = ft + 2 * hw;
 #pragma unroll
                     for (int r = 0; r < G::M / 32; ++r) {
                         const int k = NFFT == 512 ? l + 16 * r : bin640(l, r);
-                        col[k * RS] = pa[r].lo;            col[k * RS + 1] = pa[r].hi;
-                        col[(G::M - k) * RS] = pb[r].lo;   col[(G::M - k) * RS + 1] = pb[r].hi;
+                        *reinterpret_cast<P2*>(col + k * RS) = pa[r];
+                        *reinterpret_cast<P2*>(col + (G::M - k) * RS) = pb[r];
                     }
-                    if (l == 0) { col[(G::M / 2) * RS] = pmid.lo; col[(G::M / 2) * RS + 1] = pmid.hi; }
+                    if (l == 0) *reinterpret_cast<P2*>(col + (G::M / 2) * RS) = pmid;
                 }
                 __syncthreads();
                 const int f0 = 2 * it * HW;
