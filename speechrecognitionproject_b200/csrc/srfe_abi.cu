@@ -193,6 +193,10 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     mfcc_window(p, win);
     mfcc_filters(p, dense);
     mfcc_dct(p, dct);
+    // The kernel keeps the mel energies as log2 values; 10 log10(x) = kDb * log2(x) is folded into the (linear) DCT here,
+    // in double, and into the top_db threshold -- one multiply per filter and frame less in the kernel.
+    const double kDb = 10.0 * std::log10(2.0);
+    for (double& d : dct) d *= kDb;
     SparseBank sb;
     to_sparse(dense, p.n_mels, p.n_fft / 2 + 1, 0.25, sb);
     BlobBuilder bb;
@@ -204,7 +208,7 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
     e->kp.start0 = -(p.n_fft / 2);
     e->kp.n_mfcc = p.n_mfcc;
     e->kp.n_deltas = p.n_deltas;
-    e->kp.top_db = p.top_db;
+    e->kp.top_db = p.top_db >= 0.f ? (float)((double)p.top_db / kDb) : p.top_db;
     e->kp.amin = p.amin;
     e->kp.layout = p.layout;
     e->kp.tile_stride = p.n_mels | 1;                                  // P2 units, odd: conflict-free pair-row reads

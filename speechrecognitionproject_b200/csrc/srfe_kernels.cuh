@@ -55,7 +55,7 @@ struct KParams {
     int take_log, layout;
     float preemph;
     int n_mfcc, n_deltas;
-    float top_db, amin, dct_row0_sum;
+    float top_db, amin, dct_row0_sum;  // top_db in log2 units (dB / 3.0103); the DCT tables carry the 3.0103
     const float* dct_kf;               // global [n_mfcc][n_mels] DCT-II rows (generic path, odd n_mels)
     int dct_fold, off_dfold;           // folded DCT table: shared-memory offset (right after the common tables)
     int dct_cb, dct_pq, dct_nbe, dct_nbo;   //   coefficients per block, frame pairs per thread, even / odd block counts
@@ -507,8 +507,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             if (cA.ok) orowA[m] = 6.020599913279624f * lg2_ftz(a);      // 20 log10
                             if (cB.ok) orowB[m] = 6.020599913279624f * lg2_ftz(b);
                         } else {
-                            const float da = 3.010299956639812f * lg2_ftz(fmaxf(acc.lo, p.amin));   // 10 log10
-                            const float db = 3.010299956639812f * lg2_ftz(fmaxf(acc.hi, p.amin));
+                            // log2 units: the factor 10 log10(2) of power_to_db lives in the DCT tables and in top_db
+                            // (host, double precision) -- the DCT is linear and the clamp only compares
+                            const float da = lg2_ftz(fmaxf(acc.lo, p.amin));
+                            const float db = lg2_ftz(fmaxf(acc.hi, p.amin));
                             prow[m] = mkp(da, db);              // one STS.64 per filter and frame pair
                             // (frames past the end alias the clip's last valid frame -- frame_pos -- so their values are
                             //  values the maximum has seen anyway: no masking needed)
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             float gmax = (lane < (nthr >> 5)) ? s_red[lane] : -CUDART_INF_F;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-            const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip
+            const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;   // power_to_db(top_db): max over the clip (log2 units)
             // DCT-II on values re-centred per frame: with c_t = max(mean_f dB[t][f], thr),
             //   C[k][t] = sum_f D[k][f] (x[t][f] - c_t) + c_t * sum_f D[k][f],   sum_f D[k][f] = sqrt(n_mels) [k == 0]
             // so the accumulated magnitudes are the within-frame spread, not c0 ~ 1e3.
