@@ -407,6 +407,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 // the radix-4 order of bin640() for N = 640
                 auto kbin = [&](int r) { return NFFT == 512 ? l + 16 * r : bin640(l, r); };
 
+                // Stores to global rows are NOT guarded by cA.ok / cB.ok: a frame slot past the end of the group aliases the
+                // group's last valid frame (frame_pos), so it recomputes that frame bit for bit and rewrites the same row with
+                // the same values -- cheaper than a branch around every store.
                 if (FAM == FAM_SPEC) {
                     // density scaling, one-sided doubling (not DC / Nyquist), optional ln(. + eps)
                     const float s2 = 2.f * p.scale;
@@ -428,8 +431,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                                 a0 = pa[r].lo * sc; a1 = pa[r].hi * sc; b0 = pb[r].lo * sc; b1 = pb[r].hi * sc;
                             }
                             if (NFFT == 512) {              // lanes hold consecutive bins: store straight from registers
-                                if (cA.ok) { rowA[k] = a0; rowA[G::M - k] = b0; }
-                                if (cB.ok) { rowB[k] = a1; rowB[G::M - k] = b1; }
+                                rowA[k] = a0; rowA[G::M - k] = b0;
+                                rowB[k] = a1; rowB[G::M - k] = b1;
                             } else {
                                 pbuf[k] = mkp(a0, a1);
                                 pbuf[G::M - k] = mkp(b0, b1);
@@ -439,8 +442,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                         if (p.take_log) { c0 = 0.6931471805599453f * lg2_ftz(c0 + p.log_eps); c1 = 0.6931471805599453f * lg2_ftz(c1 + p.log_eps); }
                         if (NFFT == 512) {
                             if (l == 0) {
-                                if (cA.ok) rowA[G::M / 2] = c0;
-                                if (cB.ok) rowB[G::M / 2] = c1;
+                                rowA[G::M / 2] = c0;
+                                rowB[G::M / 2] = c1;
                             }
                         } else {
                             if (l == 0) pbuf[G::M / 2] = mkp(c0, c1);
@@ -448,13 +451,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
 #pragma unroll
                             for (int r = 0; r < G::M / 16; ++r) {       // natural order: 64-byte runs per half-warp
                                 const P2 q2 = pbuf[l + 16 * r];
-                                if (cA.ok) rowA[l + 16 * r] = q2.lo;
-                                if (cB.ok) rowB[l + 16 * r] = q2.hi;
+                                rowA[l + 16 * r] = q2.lo;
+                                rowB[l + 16 * r] = q2.hi;
                             }
                             if (l == 0) {
                                 const P2 q2 = pbuf[G::M];
-                                if (cA.ok) rowA[G::M] = q2.lo;
-                                if (cB.ok) rowB[G::M] = q2.hi;
+                                rowA[G::M] = q2.lo;
+                                rowB[G::M] = q2.hi;
                             }
                             __syncwarp();
                         }
@@ -504,8 +507,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             // flush-to-zero log never returns -inf (far below any level the front end can resolve)
                             a = (a == 0.f) ? 2.220446049250313e-16f : fmaxf(a, 1.17549435e-38f);
                             b = (b == 0.f) ? 2.220446049250313e-16f : fmaxf(b, 1.17549435e-38f);
-                            if (cA.ok) orowA[m] = 6.020599913279624f * lg2_ftz(a);      // 20 log10
-                            if (cB.ok) orowB[m] = 6.020599913279624f * lg2_ftz(b);
+                            orowA[m] = 6.020599913279624f * lg2_ftz(a);                 // 20 log10
+                            orowB[m] = 6.020599913279624f * lg2_ftz(b);
                         } else {
                             // log2 units: the factor 10 log10(2) of power_to_db lives in the DCT tables and in top_db
                             // (host, double precision) -- the DCT is linear and the clamp only compares
