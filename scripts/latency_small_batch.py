@@ -38,3 +38,11 @@ for _ in range(300): fns()
 torch.cuda.synchronize()
 t_eager = (time.perf_counter() - t0) / 300
 print(json.dumps({"ensemble_step_B1_three_front_ends": {"eager_us": round(t_eager * 1e6, 1), "cuda_graph_us": round(t_graph * 1e6, 1)}}))
+
+# reference-named single-clip functions on a CPU tensor (H2D -> kernel -> D2H inside the call), as a per-clip loop would call them
+xc = (torch.randn(16000) * 3000).round()
+for name, fn in (("compute_mfcc", S.compute_mfcc), ("compute_spec", S.compute_spec), ("filter_banks", S.filter_banks)):
+    for _ in range(20): fn(xc)
+    t0 = time.perf_counter()
+    for _ in range(300): y = fn(xc)
+    print(json.dumps({"single_clip_cpu_tensor": name, "per_call_us": round((time.perf_counter() - t0) / 300 * 1e6, 1), "shape": list(y.shape)}))
