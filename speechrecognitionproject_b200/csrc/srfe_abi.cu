@@ -375,7 +375,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 double eff = (double)nf / (double)(rounds * per_round);
                 if (mf && ctas == 2) eff = std::sqrt(eff);
                 double score = eff * std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
-                if (ctas == 2) score *= mf ? 1.6 : ft ? 1.1 : 0.96;
+                if (ctas == 2) score *= mf ? 1.6 : ft ? 1.1 : 0.92;
                 score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 + 0.01 * std::log2((double)cpc);
                 if (score > best + 1e-9) { best = score; bc = pl; bc.warps = warps; bc.ctas = ctas; bc.cpc = cpc; }
             }
