@@ -97,6 +97,20 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # reference arm: the reference's CPU feature path (restated librosa) on all host cores
 # ---------------------------------------------------------------------------------------
+def _host_info() -> dict:
+    """CPU model of the box and the thread settings the CPU legs ran under (SURVEY 8d asks for them next to the number)."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"cpu_model": model, "host_cores": os.cpu_count(), "omp_num_threads": os.environ.get("OMP_NUM_THREADS", "unset")}
+
+
 def _cpu_worker(args):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     seed, start, n = args
@@ -134,7 +148,7 @@ def run_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "preset": "C-MFCC", "note": "CPU reference path on host cores; bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample, **_host_info()},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -154,7 +168,8 @@ def cpu_baseline_single(budget_s: float = 12.0) -> dict:
         if el > budget_s or n >= 32768:
             break
     return {"value": n / el, "unit": "clips/s", "cores": 1, "kind": "port",
-            "sample": f"{n} clips of the seeded corpus (config 3), oracle.mfcc_ref one clip per call, {el:.1f} s, 1 thread"}
+            "sample": f"{n} clips of the seeded corpus (config 3), oracle.mfcc_ref one clip per call, {el:.1f} s, 1 thread",
+            **_host_info()}
 
 
 # ---------------------------------------------------------------------------------------
