@@ -11,8 +11,9 @@ What is pinned:
   * mfcc  : models/model_mfcc_bgru.py::compute_mfcc imported through
             oracle/librosa_shim.py (librosa itself is absent -> "restated
             librosa"); plus independent cross-checks of the restated chain
-            against transformers.audio_utils and torchaudio, recorded in
-            tests/golden/mfcc_crosscheck.json.
+            against transformers.audio_utils and torchaudio for R-MFCC and C-MFCC
+            (oracle/crosscheck.py): recomputed live by tests/test_mfcc_crosscheck.py,
+            a copy recorded in tests/golden/mfcc_crosscheck.json.
 """
 from __future__ import annotations
 
@@ -59,9 +60,9 @@ def golden_inputs() -> tuple[list[str], np.ndarray]:
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     try:                                    # import before the shim: transformers probes librosa.__spec__
-        from transformers import audio_utils
+        from transformers import audio_utils  # noqa: F401
     except Exception:                       # pragma: no cover
-        audio_utils = None
+        pass
     librosa_shim.install()
     m_spec_bgru = _load("model_spec_bgru")
     m_spec_cnn = _load("model_spec_cnn")
@@ -81,42 +82,25 @@ def main() -> None:
                         names=np.array(names), x=x,
                         spec_ft=spec_ft, spec_tf=spec_tf, fbank=fbank, mfcc=mfcc)
 
-    # ---- independent cross-checks of the restated librosa chain ----------------
-    report = {"note": "max abs difference of oracle.mfcc (static 13 coeffs, no deltas) vs independent implementations",
+    # ---- independent cross-checks of the restated librosa chain (recorded copy; the LIVE checks are
+    #      tests/test_mfcc_crosscheck.py) ----------------------------------------------------------
+    from dataclasses import replace
+    from oracle import crosscheck
+    report = {"note": "max abs difference of oracle.mfcc_truth (static coefficients) vs independent implementations; "
+                      "informational record -- tests/test_mfcc_crosscheck.py recomputes these on every run",
               "clips": names}
-    p13 = features.MfccParams(n_deltas=0)
-    ours = np.stack([features._mfcc_core(x[i].astype(np.float64), p13, quantise_stft=False) for i in range(len(names))])
-    try:
-        import scipy.fft
-        if audio_utils is None:
-            raise ImportError("transformers.audio_utils unavailable")
-        fb = audio_utils.mel_filter_bank(num_frequency_bins=321, num_mel_filters=128, min_frequency=0.0,
-                                         max_frequency=8000.0, sampling_rate=16000, norm="slaney", mel_scale="slaney")
-        report["mel_matrix_vs_transformers"] = float(np.abs(fb.T - features.slaney_mel_filterbank()).max())
-        diffs = []
-        for i in range(len(names)):
-            s = audio_utils.spectrogram(x[i].astype(np.float64), audio_utils.window_function(640, "hann"),
-                                        frame_length=640, hop_length=320, fft_length=640, power=2.0, center=True,
-                                        pad_mode="reflect", mel_filters=fb, mel_floor=1e-10, log_mel="dB",
-                                        reference=1.0, min_value=1e-10, db_range=80.0)
-            c = scipy.fft.dct(s, axis=0, type=2, norm="ortho")[:13]
-            diffs.append(float(np.abs(c - ours[i]).max()))
-        report["mfcc_vs_transformers_audio_utils"] = dict(zip(names, diffs))
-    except Exception as e:  # pragma: no cover
-        report["transformers_error"] = repr(e)
-    try:
-        import torchaudio
-        t = torchaudio.transforms.MFCC(16000, 13, log_mels=False, melkwargs=dict(
-            n_fft=640, hop_length=320, n_mels=128, norm="slaney", mel_scale="slaney", center=True,
-            pad_mode="reflect", power=2.0))
-        t = t.double()
-        diffs = []
-        for i in range(len(names)):
-            c = t(torch.from_numpy(x[i].astype(np.float64))).numpy()
-            diffs.append(float(np.abs(c - ours[i]).max()))
-        report["mfcc_vs_torchaudio_f64_with_f32_tables"] = dict(zip(names, diffs))
-    except Exception as e:  # pragma: no cover
-        report["torchaudio_error"] = repr(e)
+    for preset in ("R-MFCC", "C-MFCC"):
+        p = replace(features.PRESETS[preset], n_deltas=0)
+        ours = [features.mfcc_truth(x[i].astype(np.float64), p) for i in range(len(names))]
+        rep = {"mel_matrix_vs_transformers": float(np.abs(crosscheck.hf_mel_matrix(p).T - features.slaney_mel_filterbank(
+            p.sr, p.n_fft, p.n_mels, p.fmin, p.f_hi)).max())}
+        for key, fn in (("mfcc_vs_transformers_audio_utils", crosscheck.hf_mfcc),
+                        ("mfcc_vs_torchaudio_f64_with_f32_tables", crosscheck.torchaudio_mfcc)):
+            try:
+                rep[key] = {n: float(np.abs(fn(x[i].astype(np.float64), p) - ours[i]).max()) for i, n in enumerate(names)}
+            except Exception as e:  # pragma: no cover
+                rep[key + "_error"] = repr(e)
+        report[preset] = rep
     with open(os.path.join(OUT, "mfcc_crosscheck.json"), "w") as f:
         json.dump(report, f, indent=1)
 

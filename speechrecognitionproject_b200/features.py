@@ -52,6 +52,10 @@ class SpecParams:
     eps: float = 1e-10
     layout: str = "ft"
 
+    def op_args(self) -> tuple:
+        """positional arguments of ``torch.ops.srfe.spec`` after the PCM tensor (plain Python values: traceable)"""
+        return (self.fs, self.nperseg, self.noverlap, bool(self.log), float(self.eps), _layout_code(self.layout))
+
     def to_c(self) -> SpecParamsC:
         return SpecParamsC(self.fs, self.nperseg, self.noverlap, int(self.log), self.eps, _layout_code(self.layout))
 
@@ -65,6 +69,9 @@ class FbankParams:
     nfft: int = 512
     preemph: float = 0.97
     nfilt: int = 120
+
+    def op_args(self) -> tuple:
+        return (self.fs, self.frame_len, self.frame_step, self.nfft, float(self.preemph), self.nfilt)
 
     def to_c(self) -> FbankParamsC:
         return FbankParamsC(self.fs, self.frame_len, self.frame_step, self.nfft, self.preemph, self.nfilt)
@@ -86,6 +93,11 @@ class MfccParams:
     top_db: Optional[float] = 80.0
     amin: float = 1e-10
     layout: str = "ft"
+
+    def op_args(self) -> tuple:
+        return (self.sr, self.n_fft, self.win_length or 0, self.hop, self.n_mels, float(self.fmin),
+                float(self.fmax) if self.fmax else 0.0, self.n_mfcc, self.n_deltas,
+                -1.0 if self.top_db is None else float(self.top_db), float(self.amin), _layout_code(self.layout))
 
     def to_c(self) -> MfccParamsC:
         return MfccParamsC(self.sr, self.n_fft, self.win_length or 0, self.hop, self.n_mels, self.fmin,
@@ -130,13 +142,20 @@ def launch_count() -> int:
 # the three custom ops (CUDA only; no autograd formula: features are always computed
 # under torch.no_grad(), model_mfcc_bgru.py:29)
 # ------------------------------------------------------------------------------------
-def _prep(x: torch.Tensor) -> torch.Tensor:
+def _check_pcm(x: torch.Tensor) -> None:
     if x.dtype not in (torch.float32, torch.int16):
         raise TypeError(f"PCM must be float32 (dataset.py:117) or int16 (the wav's own type, dataset.py:103), got {x.dtype}")
     if x.dim() != 2:
         raise ValueError("expected a [n_clips, n_samples] tensor")
+
+
+def _prep(x: torch.Tensor) -> torch.Tensor:
+    """Make a [n_clips, n_samples] view the kernels can read: unit sample stride, rows that do not overlap and start on
+    a sample pair.  Only real tensors come here (the custom ops call it on their concrete inputs), never tracing fakes."""
+    _check_pcm(x)
     pair = 2 * x.element_size()                    # rows aligned to a sample pair
-    if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) % 2) or x.data_ptr() % pair:
+    if (x.stride(1) != 1 or (x.size(0) > 1 and (x.stride(0) % 2 or x.stride(0) < x.size(1)))   # odd / overlapping / expanded rows
+            or x.data_ptr() % pair):
         x = x.contiguous()
         if x.data_ptr() % pair:                    # odd-offset view of a larger buffer
             x = x.clone()
@@ -186,7 +205,7 @@ def _spec_op(pcm: torch.Tensor, fs: int, nperseg: int, noverlap: int, take_log: 
     shp = (C.c_int64 * 2)()
     _lib.check(_lib.lib().srfe_spec_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
     out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
-    _run_device("spec", cp, pcm, out)
+    _run_device("spec", cp, _prep(pcm), out)
     return out
 
 
@@ -204,7 +223,7 @@ def _fbank_op(pcm: torch.Tensor, fs: int, frame_len: int, frame_step: int, nfft:
     shp = (C.c_int64 * 2)()
     _lib.check(_lib.lib().srfe_fbank_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
     out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
-    _run_device("fbank", cp, pcm, out)
+    _run_device("fbank", cp, _prep(pcm), out)
     return out
 
 
@@ -221,7 +240,7 @@ def _mfcc_op(pcm: torch.Tensor, sr: int, n_fft: int, win_length: int, hop: int, 
     shp = (C.c_int64 * 2)()
     _lib.check(_lib.lib().srfe_mfcc_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
     out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
-    _run_device("mfcc", cp, pcm, out)
+    _run_device("mfcc", cp, _prep(pcm), out)
     return out
 
 
@@ -248,20 +267,16 @@ def _run_host(fam: str, cp, x: torch.Tensor, shape: tuple[int, int], device: Opt
 
 def _dispatch(fam: str, params, x: torch.Tensor, device: Optional[int]) -> torch.Tensor:
     single = x.dim() == 1
-    xb = _prep(x.unsqueeze(0) if single else x)
+    xb = x.unsqueeze(0) if single else x
     if xb.is_cuda and not torch.compiler.is_compiling():
-        y = _eager_device(fam, params, xb)
+        y = _eager_device(fam, params, _prep(xb))
     elif xb.is_cuda:
-        c = params.to_c()
-        if fam == "spec":
-            y = torch.ops.srfe.spec(xb, c.sample_rate, c.nperseg, c.noverlap, bool(c.take_log), c.log_eps, c.layout)
-        elif fam == "fbank":
-            y = torch.ops.srfe.fbank(xb, c.sample_rate, c.frame_len, c.frame_step, c.n_fft, c.preemph, c.nfilt)
-        else:
-            y = torch.ops.srfe.mfcc(xb, c.sample_rate, c.n_fft, c.win_length, c.hop, c.n_mels, c.fmin, c.fmax,
-                                    c.n_mfcc, c.n_deltas, c.top_db, c.amin, c.layout)
+        # under torch.compile the tensors are fakes: no data_ptr / stride fix-ups here (the op does them on the real
+        # tensors at run time), only dtype / rank checks that fakes can answer
+        _check_pcm(xb)
+        y = getattr(torch.ops.srfe, fam)(xb, *params.op_args())
     else:
-        y = _run_host(fam, params.to_c(), xb, out_shape(params, xb.size(1)), device)
+        y = _run_host(fam, params.to_c(), _prep(xb), out_shape(params, xb.size(1)), device)
     return y[0] if single else y
 
 

@@ -45,18 +45,14 @@ def test_fbank_restated_equals_reference_golden(golden):
         np.testing.assert_array_equal(got, golden["fbank"][i])
 
 
-def test_mfcc_restated_equals_shimmed_reference_golden(golden):
+def test_mfcc_golden_is_the_shim_path_selfcheck(golden):
+    """NOT an independent pin: golden['mfcc'] is the unmodified compute_mfcc (models/model_mfcc_bgru.py:11-19) run
+    with librosa replaced by oracle/librosa_shim.py, i.e. the restatement seen through the reference's own wrapper
+    (tensor conversion, np.gradient calls, concatenation order, float32 cast).  The independent evidence for the
+    librosa arithmetic is live in tests/test_mfcc_crosscheck.py."""
     x = golden["x"]
     for i in range(x.shape[0]):
         np.testing.assert_array_equal(oracle.mfcc_ref(x[i]), golden["mfcc"][i])
-
-
-def test_mfcc_crosschecks_recorded():
-    with open(os.path.join(ROOT, "tests", "golden", "mfcc_crosscheck.json")) as f:
-        rep = json.load(f)
-    assert rep["mel_matrix_vs_transformers"] < 1e-12
-    assert max(rep["mfcc_vs_transformers_audio_utils"].values()) < 5e-4        # HF stores its STFT as complex64
-    assert max(rep["mfcc_vs_torchaudio_f64_with_f32_tables"].values()) < 5e-4  # torchaudio tables are float32
 
 
 def test_truth_vs_reference_dtype_paths(golden):
