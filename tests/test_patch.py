@@ -272,3 +272,73 @@ def test_shared_front_end_gpu(srfe_lib):
         torch.testing.assert_close(got[k].cpu(), want[k], rtol=tol, atol=tol, msg=lambda m, k=k: f"{k}: {m}")
     for m in mods.values():
         patch.unpatch_model(m)
+
+
+# ---- the full-size model_mfcc_bgru (BASELINE cfg5) pinned to the UNMODIFIED reference module -----------------------
+def _golden_logits():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_mfcc_bgru_logits.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def _seeded_net(mod, seed):
+    torch.manual_seed(int(seed))
+    return mod.Network().eval()
+
+
+def _assert_checksums(net, g):
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    for k, want in zip(g["keys"], g["checksums"]):
+        v = sd[str(k)].double()
+        np.testing.assert_allclose([float(v.sum()), float(v.abs().sum())], want, rtol=0, atol=0, err_msg=str(k))
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_twin_regenerates_the_reference_weights_and_logits():
+    """tests/twins.py's shape twin, seeded like oracle/make_golden_logits.py seeded the unmodified reference module,
+    has the reference's parameters bit for bit (per-tensor checksums recorded from the real module) and its forward
+    (per-clip CPU loop, oracle features) returns the recorded reference logits."""
+    from tests import twins
+    g = _golden_logits()
+    net = _seeded_net(twins.twin_model_mfcc_bgru(), g["seed"])
+    _assert_checksums(net, g)
+    x = torch.from_numpy(oracle.synthetic_corpus(int(g["n_clips"]), config_index=int(g["config_index"])))
+    with torch.no_grad():
+        np.testing.assert_allclose(net(x).numpy(), g["logits"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.filterwarnings("ignore")
+def test_twin_equals_reference_module():
+    from tests import twins
+    g = _golden_logits()
+    ref = _seeded_net(twins.load_reference("model_mfcc_bgru"), g["seed"])
+    twin = _seeded_net(twins.twin_model_mfcc_bgru(), g["seed"])
+    _assert_checksums(ref, g)
+    for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), twin.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+@pytest.mark.gpu
+@pytest.mark.filterwarnings("ignore")
+def test_full_size_model_mfcc_bgru_gpu_vs_reference_logits(srfe_lib):
+    """cfg5's model at full size on the GPU: reference weights (regenerated from the seed, checksummed), forward
+    re-plumbed by patch_model (PCM H2D -> fused MFCC kernel -> cuDNN BGRU), logits against the ones the UNMODIFIED
+    reference module produced on the CPU (tests/golden/model_mfcc_bgru_logits.npz)."""
+    from tests import twins
+    g = _golden_logits()
+    mod, which = twins.load("model_mfcc_bgru")
+    net = _seeded_net(mod, g["seed"])
+    _assert_checksums(net, g)
+    net = net.cuda()
+    patch.patch_model(mod)
+    try:
+        x = torch.from_numpy(oracle.synthetic_corpus(int(g["n_clips"]), config_index=int(g["config_index"])))
+        with torch.no_grad():
+            got = net(x)
+            got_dev = net(x.cuda())
+        assert got.is_cuda and torch.equal(got, got_dev)
+        # features differ from the CPU path by <= 1e-3 (MFCC tolerance); TF32 is off for cuDNN RNNs by default
+        np.testing.assert_allclose(got.cpu().numpy(), g["logits"], rtol=0, atol=2e-3, err_msg=which)
+    finally:
+        patch.unpatch_model(mod)
