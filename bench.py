@@ -37,6 +37,15 @@ WORKLOAD = ("cfg4: MFCC (40 coeffs, win 400 / hop 160 / n_fft 512, 128 slaney me
             "synthetic 16 kHz corpus sharded by clip across the GPUs")
 
 
+def make_config(args, world: int) -> dict:
+    """the `config` object of the JSON line -- the same keys and values for both arms (the driver compares them)"""
+    per_gpu = (args.clips + world - 1) // world
+    return {"workload": WORKLOAD, "preset": args.preset, "corpus_clips": args.clips, "clips_per_gpu": per_gpu,
+            "n_samples": N_SAMPLES, "parallelism": f"clip-sharded x{world}, no collective",
+            "l2": "inputs (>= 2 GB per GPU) larger than the 126 MB L2; every step re-reads the whole shard",
+            "e2e_clips_per_gpu_per_step": min(args.e2e_clips, per_gpu)}
+
+
 # ---------------------------------------------------------------------------------------
 # clocks sampler (recipe: /opt/skills/guides/B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------
@@ -111,13 +120,25 @@ def _host_info() -> dict:
     return {"cpu_model": model, "host_cores": os.cpu_count(), "omp_num_threads": os.environ.get("OMP_NUM_THREADS", "unset")}
 
 
-def _cpu_worker(args):
+_WORKER_CLIPS = {}
+
+
+def _cpu_prepare(args):
+    """untimed: synthesise this worker's clips for one step (the native arm builds its corpus outside its timer too)"""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seed, start, n = args
+    key, start, n = args
     import oracle
-    x = oracle.synthetic_corpus(n, config_index=3, start=start)
+    _WORKER_CLIPS[key] = oracle.synthetic_corpus(n, config_index=3, start=start)
+    oracle.mfcc_ref(_WORKER_CLIPS[key][0], oracle.C_MFCC)        # import / table warm-up
+    return os.getpid()
+
+
+def _cpu_worker(key):
+    """timed: the reference's per-clip feature call, one clip per call like Network.forward's loop"""
+    import oracle
+    x = _WORKER_CLIPS.pop(key)
     t0 = time.perf_counter()
-    for i in range(n):
+    for i in range(x.shape[0]):
         oracle.mfcc_ref(x[i], oracle.C_MFCC)
     return time.perf_counter() - t0
 
@@ -130,26 +151,36 @@ def run_reference(args) -> None:
     cores = os.cpu_count() or 1
     per_worker = 128
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    # one single-worker pool per core: a job prepared on worker w is also computed on worker w
+    pools = [ctx.Pool(1) for _ in range(cores)]
+    try:
         def step(k):
-            jobs = [(k, (k * cores + w) * per_worker, per_worker) for w in range(cores)]
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, jobs)
-            return time.perf_counter() - t0
+            prep = [pl.apply_async(_cpu_prepare, ((k, (k * cores + w) * per_worker, per_worker),)) for w, pl in enumerate(pools)]
+            for r in prep:
+                r.get()
+            t0 = time.perf_counter()                                 # ---- timed region: feature calls only ----
+            res = [pl.apply_async(_cpu_worker, (k,)) for pl in pools]
+            worker_s = [r.get() for r in res]
+            return time.perf_counter() - t0, max(worker_s)
         for k in range(args.warmup):
             step(k)
         times = [step(args.warmup + k) for k in range(args.steps)]
-    total = sum(times)
+    finally:
+        for pl in pools:
+            pl.terminate()
+    total = sum(t for t, _ in times)
     clips = cores * per_worker * args.steps
     value = clips / total
-    sample = f"{per_worker} clips x {cores} worker processes per step, oracle.mfcc_ref (restated librosa-0.6 chain), C-MFCC"
+    sample = (f"{per_worker} clips x {cores} worker processes per step, oracle.mfcc_ref (restated librosa-0.6 chain), C-MFCC; "
+              "timed region = the feature calls only (clip synthesis and worker start-up outside), wall clock around all workers")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "preset": "C-MFCC", "note": "CPU reference path on host cores; bounded sample"},
+        "config": make_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample, **_host_info(),
-                         "omp_num_threads": "1 per worker process"},
+                         "omp_num_threads": "1 per worker process",
+                         "slowest_worker_compute_s_per_step": sum(m for _, m in times) / args.steps},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -188,6 +219,46 @@ def synth_shard(n_clips: int, device, seed: int):
         sigma = torch.exp(torch.empty((m, 1), device=device).uniform_(3.4012, 8.9872, generator=g))
         x[i:i + m] = (torch.randn((m, N_SAMPLES), device=device, generator=g) * sigma).clamp_(-32768, 32767).round_()
     return x
+
+
+def preset_table(S, x, peak: float) -> dict:
+    """Every parameter set at the batch sizes BASELINE.json's configs quote (cfg2: C-FBANK B=1024; cfg3: C-SPEC B=4096)
+    and at 16,384 clips: CUDA events around every launch; the L2 (126 MB) is flushed before each timed launch by
+    rewriting a 256 MB buffer, so small batches cannot be served from cache."""
+    import torch
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=x.device)
+    cases = [(name, p, None, 16384) for name, p in S.PRESETS.items()]
+    cases += [("R-SPEC", S.R_SPEC, "tf", 16384), ("C-SPEC", S.C_SPEC, "tf", 16384),
+              ("C-FBANK", S.C_FBANK, None, 1024), ("R-FBANK", S.R_FBANK, None, 1024),
+              ("C-SPEC", S.C_SPEC, None, 4096), ("C-SPEC", S.C_SPEC, "tf", 4096),
+              ("R-SPEC", S.R_SPEC, None, 4096), ("R-SPEC", S.R_SPEC, "tf", 4096),
+              ("R-MFCC", S.R_MFCC, "tf", 8192), ("C-MFCC", S.C_MFCC, None, 64)]
+    rows = {}
+    for name, p, layout, nclips in cases:
+        fam = type(p).__name__
+        f2 = {"SpecParams": S.spec, "FbankParams": S.fbank, "MfccParams": S.mfcc}[fam]
+        kw = {"layout": layout} if layout else {}
+        xs = x[:nclips]
+        for _ in range(3):
+            f2(xs, p, **kw)
+        reps = 10 if nclips >= 4096 else 30
+        evs = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            f2(xs, p, **kw)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        med = ms[len(ms) // 2]
+        cps = xs.size(0) / (med * 1e-3)
+        gbs = cps * S.bytes_per_clip(p, N_SAMPLES) / 1e9
+        lay = layout or getattr(p, "layout", "tf")
+        rows[f"{name}/{lay}/B{nclips}"] = {"clips_per_s": cps, "GBps": gbs, "hbm_frac": gbs / peak, "ms_median": med,
+                                           "ms_best": ms[0], "launches": reps}
+    return rows
 
 
 def run_native(args) -> None:
@@ -282,6 +353,37 @@ def run_native(args) -> None:
     if world > 1:
         dist.all_reduce(te16, op=dist.ReduceOp.MAX)
     e2e16_value = world * e2e_clips * e2e_steps / float(te16.item())
+    # same float32 handoff from PAGEABLE host memory -- what the reference's DataLoader hands over (training.py:77: no
+    # pin_memory); libsrfe stages it through its own pinned ring (srfe_abi.cu: run_host)
+    xpg = torch.empty((e2e_clips, N_SAMPLES), dtype=torch.float32)
+    xpg.copy_(xh)
+    assert not xpg.is_pinned()
+    for _ in range(2):
+        yh = fn(xpg, preset)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        yh = fn(xpg, preset)
+    torch.cuda.synchronize()
+    tep = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tep, op=dist.ReduceOp.MAX)
+    e2e_pageable_value = world * e2e_clips * e2e_steps / float(tep.item())
+    # the box's host->device ceiling: the same pinned bytes copied with NO kernel, all ranks at once (e2e is bound by
+    # this, not by a collective: aggregate H2D through one host's memory system / PCIe root complexes)
+    xdev = torch.empty_like(xh, device=dev)
+    for _ in range(2):
+        xdev.copy_(xh, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        xdev.copy_(xh, non_blocking=True)
+    torch.cuda.synchronize()
+    th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    h2d_gbs = world * e2e_clips * N_SAMPLES * 4 * e2e_steps / float(th.item()) / 1e9
+    del xdev, xpg
 
     if rank == 0:
         value = args.clips * args.steps / (total_ms_max * 1e-3)
@@ -293,53 +395,43 @@ def run_native(args) -> None:
                 peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
         except Exception:
             pass
-        traffic = None
-        try:
+        traffic, traffic_src = None, None
+        try:                       # not measurable inside a timed run: taken from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tr = json.load(f).get(args.preset)
+                tj = json.load(f)
+            tr = tj.get(args.preset)
             if tr:
                 traffic = tr["dram_bytes_per_clip"] * (b1 - b0)
+                traffic_src = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per clip from the ncu "
+                               f"--set full capture {tr.get('source', tj.get('source', '?'))}, scaled to this launch; not measured in this run")
         except Exception:
             pass
         out = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "preset": args.preset, "corpus_clips": args.clips,
-                       "clips_per_gpu": b1 - b0, "n_samples": N_SAMPLES, "parallelism": f"clip-sharded x{world}, no collective",
-                       "l2": "inputs (>= 2 GB per GPU) larger than the 126 MB L2; every step re-reads the whole shard",
-                       "e2e_clips_per_gpu_per_step": e2e_clips},
+            "config": make_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_clip": bpc,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_clip": bpc,
                          "kernel_ms_avg": avg_kern_ms, "kernel": "srfe_kernel<512, MFCC>",
                          "note": "FP32-pipe bound, not HBM bound: see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(e2e_clips * N_SAMPLES * 4),
                     "d2h_bytes_per_step": d2h},
             "e2e_int16_ingest": {"value": e2e16_value, "unit": "clips/s", "h2d_bytes_per_step": int(e2e_clips * N_SAMPLES * 2),
                                  "d2h_bytes_per_step": d2h, "note": "extra: int16 host PCM (wav native type), converted in-kernel"},
+            "e2e_pageable_host": {"value": e2e_pageable_value, "unit": "clips/s",
+                                  "note": "extra: float32 PCM in pageable host memory (the reference's DataLoader handoff, "
+                                          "training.py:77), staged through libsrfe's pinned ring"},
+            "e2e_h2d_ceiling": {"GBps": h2d_gbs, "clips_per_s": h2d_gbs * 1e9 / (N_SAMPLES * 4), "e2e_frac": e2e_value / (h2d_gbs * 1e9 / (N_SAMPLES * 4)),
+                                "note": "pinned float32 H2D copies of the e2e batch with no kernel, all ranks concurrently, "
+                                        "max over ranks: the ceiling e2e (float32 ingest) can reach on this box"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_single()
-        if args.all_presets:
-            xs = x[:16384]
-            extra = {}
-            for name, p in S.PRESETS.items():
-                f2 = {"SpecParams": S.spec, "FbankParams": S.fbank, "MfccParams": S.mfcc}[type(p).__name__]
-                for _ in range(3):
-                    f2(xs, p)
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(10):
-                    f2(xs, p)
-                b.record()
-                torch.cuda.synchronize()
-                cps = xs.size(0) * 10 / (a.elapsed_time(b) * 1e-3)
-                gbs = cps * S.bytes_per_clip(p, N_SAMPLES) / 1e9
-                extra[name] = {"clips_per_s": cps, "GBps": gbs, "hbm_frac": gbs / peak}
-            out["presets_16384_clips"] = extra
+        if world == 1 and not args.no_presets:
+            out["presets"] = preset_table(S, x, peak)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -355,7 +447,7 @@ def main() -> None:
     ap.add_argument("--clips", type=int, default=CORPUS_CLIPS, help="total corpus size (all GPUs)")
     ap.add_argument("--e2e-clips", type=int, default=16384, help="host-buffer batch per GPU per e2e step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--all-presets", action="store_true", help="also time every preset on 16384 clips (extra key)")
+    ap.add_argument("--no-presets", action="store_true", help="skip the per-preset table (extra key `presets`, N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -149,8 +149,12 @@ int srfe_mfcc_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64
                    const srfe_mfcc_params* p, float* out, void* cuda_stream);
 
 /* ---- host entry points (pcm/out are HOST pointers; synchronous) ----------- */
-/* H2D of the batch, the same kernels, D2H of the features, on `device`.
- * Uses a per-thread pinned staging + device workspace that grows on demand. */
+/* H2D of the batch, the same kernels, D2H of the features, on `device`, chunked over two streams so that the
+ * transfers of one chunk overlap the kernel of the other.  Pinned (page-locked) caller buffers are copied from / to
+ * directly; PAGEABLE buffers -- what the reference's DataLoader hands over, training.py:77 has no pin_memory -- are
+ * gathered by a few host threads into a pinned staging ring first (and the features scattered back from one).  The
+ * workspace (2 streams, device in / out buffers, staging buffers when needed) is per device, grows on demand, is
+ * guarded by a per-device mutex and is freed by srfe_release_host_workspace(). */
 int srfe_spec_host_f32 (const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                         const srfe_spec_params* p, float* out, int device);
 int srfe_fbank_host_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
@@ -165,7 +169,15 @@ int srfe_fbank_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, 
 int srfe_mfcc_host_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                         const srfe_mfcc_params* p, float* out, int device);
 
+/* frees the host entry points' per-device workspaces (streams, device buffers, pinned staging); they are re-created on
+ * the next host call.  Returns SRFE_OK. */
+int srfe_release_host_workspace(void);
+
 /* ---- introspection for benchmarks / tests --------------------------------- */
+/* Launch-shape override for tests and tuning sweeps: `name` in {"warps", "ctas", "cpc", "dct_cb", "dct_pq",
+ * "mfcc_tc"}, value 0 = automatic (the default).  Results never depend on these (the parity suite checks it);
+ * "mfcc_tc": 1 = force the classic CUDA-core MFCC kernel, 2 = require the tcgen05 one.  Process-wide, thread-safe. */
+int srfe_set_tuning(const char* name, int value);
 /* number of kernel launches issued by this process through the entry points */
 int64_t srfe_launch_count(void);
 /* algorithmic bytes per clip (fp32 PCM in + fp32 features out), SURVEY.md 8d */
@@ -175,7 +187,7 @@ int64_t srfe_mfcc_bytes_per_clip (const srfe_mfcc_params*  p, int64_t n_samples)
 
 /* device (global-memory) workspace the device entry points need for this call: always 0 -- PCM to features runs in
  * registers and shared memory; returns a negative srfe_status for invalid parameters.  (Host entry points keep a
- * per-thread pinned staging + device buffer of their own.) */
+ * per-device workspace of their own, see above.) */
 int64_t srfe_spec_workspace_bytes (const srfe_spec_params*  p, int64_t n_clips, int64_t n_samples);
 int64_t srfe_fbank_workspace_bytes(const srfe_fbank_params* p, int64_t n_clips, int64_t n_samples);
 int64_t srfe_mfcc_workspace_bytes (const srfe_mfcc_params*  p, int64_t n_clips, int64_t n_samples);

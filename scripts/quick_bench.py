@@ -1,11 +1,13 @@
 """Quick per-preset kernel timing (device-resident input, CUDA events). Dev tool, not the bench."""
-import sys, json, torch
+import os, sys, json, torch
 sys.path.insert(0, ".")
 import speechrecognitionproject_b200 as S
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(S.PRESETS)
 x = (torch.randn(B, 16000, device="cuda") * 3000).round()
+if len(sys.argv) > 3:                      # e.g. "warps=8,ctas=2,cpc=1" -> srfe_set_tuning
+    S.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in sys.argv[3].split(","))})
 PEAK = 6460.5
 for name in names:
     from dataclasses import replace

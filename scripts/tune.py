@@ -1,4 +1,4 @@
-"""Sweep launch configurations (SRFE_WARPS / SRFE_CTAS / SRFE_CPC) per preset. Dev tool."""
+"""Sweep launch configurations (srfe_set_tuning: warps / ctas / cpc) per preset. Dev tool."""
 import os, sys, json, itertools, torch
 sys.path.insert(0, ".")
 import speechrecognitionproject_b200 as S
@@ -22,15 +22,14 @@ for name in names:
     p = S.PRESETS[base]
     if lay: p = replace(p, layout=lay)
     fn = {"SpecParams": S.spec, "FbankParams": S.fbank, "MfccParams": S.mfcc}[type(p).__name__]
-    for k in ("SRFE_WARPS", "SRFE_CTAS", "SRFE_CPC"): os.environ.pop(k, None)
+    S.set_tuning()
     res = [("default", run(fn, p))]
     cpcs = [0] if type(p).__name__ == "MfccParams" else [1, 2, 4, 8]
     grid = [(c, w, 0) for c in (1,) for w in range(8, 17)] + [(2, w, 0) for w in range(4, 9)] + [(3, w, 0) for w in range(3, 6)] + [(4, w, 0) for w in range(2, 5)] if os.environ.get("TUNE_FINE") else None
     for ctas, warps, pf in grid or [(2, 4, 0), (2, 5, 0), (2, 6, 0), (2, 7, 0), (2, 8, 0), (2, 4, 1), (2, 5, 1), (2, 6, 1), (1, 8, 0), (1, 10, 0), (1, 12, 0), (1, 14, 0), (1, 16, 0), (1, 8, 1), (1, 10, 1), (1, 12, 1), (3, 4, 0), (3, 5, 0)]:
         best = None
         for cpc in cpcs:
-            os.environ.update(SRFE_WARPS=str(warps), SRFE_CTAS=str(ctas))
-            if cpc: os.environ["SRFE_CPC"] = str(cpc)
+            S.set_tuning(warps=warps, ctas=ctas, cpc=cpc)
             r = run(fn, p)
             if r and (best is None or r > best[0]): best = (r, cpc)
         if best: res.append((f"ctas{ctas} w{warps} pf{pf} cpc{best[1]}", best[0]))

@@ -42,6 +42,8 @@ SYMBOLS = {
     "srfe_last_error_string": (C.c_char_p, []),
     "srfe_device_count": (_i32, []),
     "srfe_launch_count": (_i64, []),
+    "srfe_release_host_workspace": (_i32, []),
+    "srfe_set_tuning": (_i32, [C.c_char_p, _i32]),
     "srfe_spec_out_shape": (_i64, [C.POINTER(SpecParamsC), _i64, _SHAPE]),
     "srfe_fbank_out_shape": (_i64, [C.POINTER(FbankParamsC), _i64, _SHAPE]),
     "srfe_mfcc_out_shape": (_i64, [C.POINTER(MfccParamsC), _i64, _SHAPE]),

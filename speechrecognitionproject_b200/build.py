@@ -18,7 +18,10 @@ OUT = os.path.join(HERE, "libsrfe.so")
 SOURCES = ["srfe_abi.cu", "srfe_tables.cpp"]
 HEADERS = ["srfe_kernels.cuh", "srfe_fft.cuh", "srfe_tables.h", os.path.join("..", "..", "include", "srfe.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC"]
+              "--shared", "-Xcompiler", "-fPIC",
+              # the CUDA runtime as a shared library (the one torch has already loaded, else the toolkit's): the artefact
+              # then carries no copy of the runtime's entry-point table
+              "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _nvcc() -> str:

@@ -9,7 +9,9 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -59,9 +61,8 @@ struct Key {
     }
 };
 
-static std::mutex g_mu;
+static std::shared_mutex g_mu;                      // readers (every launch) share; table / configuration builds are exclusive
 static std::map<Key, Entry*> g_cache;
-static std::map<const void*, int> g_attr_set;      // kernel function -> max-smem attribute raised (per process)
 
 static int align16(int x) { return (x + 15) & ~15; }
 
@@ -139,7 +140,12 @@ static int get_entry(int family, const P& p, Entry** out) {
     cudaError_t ce = cudaGetDevice(&dev);
     if (ce != cudaSuccess) return fail(SRFE_ERR_NO_DEVICE, std::string("cudaGetDevice: ") + cudaGetErrorString(ce));
     Key key{dev, family, std::string((const char*)&p, sizeof(P))};
-    std::lock_guard<std::mutex> lk(g_mu);
+    {
+        std::shared_lock<std::shared_mutex> rl(g_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) { *out = it->second; return SRFE_OK; }
+    }
+    std::unique_lock<std::shared_mutex> lk(g_mu);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) { *out = it->second; return SRFE_OK; }
     Entry* e = new Entry();
@@ -251,48 +257,52 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
 // ------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------
-struct DevInfo { int sms = 0; int smem_optin = 0; };
-static DevInfo g_dev[64];
+constexpr int kMaxDevices = 64;
+struct DevInfo { int sms = 0; int smem_optin = 0; int index = 0; };
+static DevInfo g_dev[kMaxDevices];
 
 static int dev_info(DevInfo** out) {
     int dev = 0;
     SRFE_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev[dev].sms == 0) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
+    static std::atomic<int> ready[kMaxDevices];
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        std::unique_lock<std::shared_mutex> lk(g_mu);
+        g_dev[dev].index = dev;
         SRFE_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
         SRFE_CUDA(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        ready[dev].store(1, std::memory_order_release);
     }
     *out = &g_dev[dev];
     return SRFE_OK;
 }
 
 template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
-static int launch_k(const KParams& kp, int grid, int threads, int smem_bytes, cudaStream_t st) {
+static int launch_k(const KParams& kp, int dev, int grid, int threads, int smem_bytes, cudaStream_t st) {
     auto kern = srfe_kernel<NFFT, FAM, JLO, JHI, NG, CODE, SAMP>;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const void* tag = (const char*)(const void*)kern + dev;      // per (kernel, device)
-        if (g_attr_set[tag] < smem_bytes) {                          // raise the opt-in limit on demand
-            SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            g_attr_set[tag] = smem_bytes;
-        }
+    // opt-in shared-memory limit of this instantiation, raised on demand, per device; lock-free on the hot path
+    // (two threads racing here both set a sufficient value: the attribute only ever grows)
+    static std::atomic<int> attr_set[kMaxDevices];
+    if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
+        SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int cur = attr_set[dev].load(std::memory_order_relaxed);
+        while (cur < smem_bytes && !attr_set[dev].compare_exchange_weak(cur, smem_bytes, std::memory_order_release)) {}
     }
     kern<<<grid, threads, smem_bytes, st>>>(kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "srfe_kernel launch");
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return SRFE_OK;
 }
 
 struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var, dct_pq; };
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
+// Launch-shape overrides (srfe_set_tuning; 0 = automatic).  A test / tuning hook: results never depend on them
+// (tests/test_parity_gpu.py::test_results_do_not_depend_on_launch_configuration); no environment is read on the hot path.
+enum Tuning { TUNE_WARPS = 0, TUNE_CTAS, TUNE_CPC, TUNE_DCT_CB, TUNE_DCT_PQ, TUNE_MFCC_TC, TUNE_COUNT };
+static const char* const kTuningNames[TUNE_COUNT] = {"warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc"};
+static std::atomic<int> g_tune[TUNE_COUNT];
+static int tune(int which) { return g_tune[which].load(std::memory_order_relaxed); }
 
 // Shared-memory plan of a CTA with `warps` warps:  [tables][FFT scratch][MFCC pair-row dB tile + pair means]
 // The MFCC epilogue reuses the FFT scratch for the coefficient tile; delta rows may spill into the (dead) dB tile.
@@ -321,9 +331,9 @@ static int smem_plan(const Entry* e, const KParams& kp, int warps, int budget, C
                 if (best < 0 || cost < best) { best = cost; c->dct_var = (int)i; c->dct_pq = pq; }
             }
         }
-        if (env_int("SRFE_DCT_CB", 0) > 0)                             // developer override (tuning only)
-            for (size_t i = 0; i < e->dct_vars.size(); ++i) if (e->dct_vars[i].cb == env_int("SRFE_DCT_CB", 0)) c->dct_var = (int)i;
-        if (env_int("SRFE_DCT_PQ", 0) > 0) c->dct_pq = std::min(2, env_int("SRFE_DCT_PQ", 0));
+        if (tune(TUNE_DCT_CB) > 0)                                     // override (srfe_set_tuning)
+            for (size_t i = 0; i < e->dct_vars.size(); ++i) if (e->dct_vars[i].cb == tune(TUNE_DCT_CB)) c->dct_var = (int)i;
+        if (tune(TUNE_DCT_PQ) > 0) c->dct_pq = std::min(2, tune(TUNE_DCT_PQ));
         blob = align16(e->blob_common + e->dct_vars[c->dct_var].bytes);
     }
     c->blob = blob;
@@ -382,8 +392,8 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
         }
     }
     if (best < 0) return fail(SRFE_ERR_TOO_LARGE, "clip too long: the per-clip tile does not fit in shared memory");
-    // developer overrides (tuning only)
-    const int ow = env_int("SRFE_WARPS", 0), oc = env_int("SRFE_CTAS", 0), op = env_int("SRFE_CPC", 0);
+    // overrides (srfe_set_tuning)
+    const int ow = tune(TUNE_WARPS), oc = tune(TUNE_CTAS), op = tune(TUNE_CPC);
     if (ow > 0 || oc > 0 || op > 0) {
         const int w_ = ow > 0 ? std::min(kMaxThreads / 32, std::max(1, ow)) : bc.warps;
         const int c_ = oc > 0 ? std::min(8, std::max(1, oc)) : bc.ctas;
@@ -391,7 +401,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
         const int budget = std::min(di.smem_optin, per_sm / c_ - 1024);
         const int smem = smem_plan(e, kp, w_, budget, &bc);
         bc.warps = w_; bc.ctas = c_; bc.cpc = p_;
-        if (smem < 0 || smem > budget) return fail(SRFE_ERR_TOO_LARGE, "SRFE_WARPS / SRFE_CTAS override does not fit in shared memory");
+        if (smem < 0 || smem > budget) return fail(SRFE_ERR_TOO_LARGE, "srfe_set_tuning: the warps / ctas override does not fit in shared memory");
     }
     *out = bc;
     return SRFE_OK;
@@ -414,13 +424,12 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     Config cfg;
     {   // the choice depends on (parameter set, frames per clip, batch size up to the point where the grid is full):
         // remember it -- small-batch callers (the reference's ensemble drivers run batch_size = 1) pay for the search once
-        static const char* const kOverrides[] = {"SRFE_WARPS", "SRFE_CTAS", "SRFE_CPC", "SRFE_DCT_CB", "SRFE_DCT_PQ"};
         bool overridden = false;
-        for (const char* k : kOverrides) { const char* v = getenv(k); overridden = overridden || (v && *v); }
+        for (int k = TUNE_WARPS; k <= TUNE_DCT_PQ; ++k) overridden = overridden || tune(k) > 0;
         const ConfigKey key{e, kp.T, std::min(kp.n_clips, 16 * di->sms), kp.layout, di};   // beyond that every cpc is allowed
         bool hit = false;
         if (!overridden) {
-            std::lock_guard<std::mutex> lk(g_mu);
+            std::shared_lock<std::shared_mutex> lk(g_mu);
             auto it = g_configs.find(key);
             if (it != g_configs.end()) { cfg = it->second; hit = true; }
         }
@@ -428,7 +437,7 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
             rc = pick_config(e, kp, *di, &cfg);
             if (rc != SRFE_OK) return rc;
             if (!overridden) {
-                std::lock_guard<std::mutex> lk(g_mu);
+                std::unique_lock<std::shared_mutex> lk(g_mu);
                 if (g_configs.size() >= 4096) g_configs.clear();    // variable-length callers: bounded memory
                 g_configs[key] = cfg;
             }
@@ -447,7 +456,9 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     }
     kp.sm_ctile = cfg.ctile_off;
     kp.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)kp.T - 1) / (unsigned long long)kp.T);
-    kp.debug = env_int("SRFE_DEBUG", 0);
+#ifdef SRFE_DEV
+    { const char* v = getenv("SRFE_DEBUG"); kp.debug = (v && *v) ? atoi(v) : 0; }   // developer build only: phase-skipping switches
+#endif
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
     // Curated instantiation list.  Window extents (units of 32 samples) and the preset shapes of the mel
@@ -457,8 +468,8 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
     const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
 #define SRFE_GO(N, FAM, JLO, JHI, NG, CODE)                                                                      \
-    return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, short>(kp, grid, threads, smem, st)                        \
-               : launch_k<N, FAM, JLO, JHI, NG, CODE, float>(kp, grid, threads, smem, st)
+    return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, short>(kp, di->index, grid, threads, smem, st)             \
+               : launch_k<N, FAM, JLO, JHI, NG, CODE, float>(kp, di->index, grid, threads, smem, st)
     if (e->n_fft == 512) {
         switch (e->family) {
             case FAM_SPEC: SRFE_GO(512, FAM_SPEC, 0, 16, 0, 0u);
@@ -519,32 +530,81 @@ static int run_device(int family, const void* pcm, bool i16, int64_t n_clips, in
 // ------------------------------------------------------------------------------
 // host-buffer path: chunked H2D -> kernel -> D2H on two streams
 // ------------------------------------------------------------------------------
+// One workspace per device (not per thread): two streams, two device in / out buffers and -- only when a caller hands
+// over PAGEABLE memory, which is what the reference's DataLoader does (training.py:77, no pin_memory) -- two pinned
+// staging buffers each way.  A per-device mutex serialises host-path calls on the same GPU (they would share its
+// PCIe link anyway); srfe_release_host_workspace() frees everything.
 struct HostWs {
-    int device = -1;
+    std::mutex mu;
+    bool init = false;
     cudaStream_t st[2] = {nullptr, nullptr};
     void* d_in[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
-    size_t cap_in = 0, cap_out = 0;
+    void* h_in[2] = {nullptr, nullptr};         // pinned staging (pageable callers only)
+    float* h_out[2] = {nullptr, nullptr};
+    size_t cap_in = 0, cap_out = 0, cap_hin = 0, cap_hout = 0;
 };
-static thread_local HostWs g_ws[16];
+static HostWs g_ws[kMaxDevices];
 
-static int host_ws(int device, size_t in_bytes, size_t out_bytes, HostWs** out) {
-    if (device < 0 || device >= 16) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
-    HostWs& w = g_ws[device];
-    if (w.device < 0) {
-        for (int i = 0; i < 2; ++i) SRFE_CUDA(cudaStreamCreateWithFlags(&w.st[i], cudaStreamNonBlocking));
-        w.device = device;
+template <typename T, typename AllocFn, typename FreeFn>
+static int grow_pair(T* ptr[2], size_t& cap, size_t bytes, AllocFn alloc, FreeFn release, const char* what) {
+    if (bytes <= cap) return SRFE_OK;
+    for (int i = 0; i < 2; ++i) { if (ptr[i]) release(ptr[i]); ptr[i] = nullptr; }
+    cap = 0;                                     // nothing usable until both allocations succeed
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = alloc((void**)&ptr[i], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();                  // do not leave the error for the next launch to trip over
+            for (int j = 0; j < 2; ++j) { if (ptr[j]) release(ptr[j]); ptr[j] = nullptr; }
+            return cuda_fail(e, what);
+        }
     }
-    if (in_bytes > w.cap_in) {
-        for (int i = 0; i < 2; ++i) { if (w.d_in[i]) cudaFree(w.d_in[i]); SRFE_CUDA(cudaMalloc(&w.d_in[i], in_bytes)); }
-        w.cap_in = in_bytes;
-    }
-    if (out_bytes > w.cap_out) {
-        for (int i = 0; i < 2; ++i) { if (w.d_out[i]) cudaFree(w.d_out[i]); SRFE_CUDA(cudaMalloc(&w.d_out[i], out_bytes)); }
-        w.cap_out = out_bytes;
-    }
-    *out = &w;
+    cap = bytes;
     return SRFE_OK;
+}
+
+static int host_ws_prepare(HostWs& w, size_t in_bytes, size_t out_bytes, bool stage_in, bool stage_out) {
+    if (!w.init) {
+        for (int i = 0; i < 2; ++i) SRFE_CUDA(cudaStreamCreateWithFlags(&w.st[i], cudaStreamNonBlocking));
+        w.init = true;
+    }
+    auto dmalloc = [](void** q, size_t n) { return cudaMalloc(q, n); };
+    auto dfree = [](void* q) { cudaFree(q); };
+    auto hmalloc = [](void** q, size_t n) { return cudaMallocHost(q, n); };
+    auto hfree = [](void* q) { cudaFreeHost(q); };
+    int rc = grow_pair(w.d_in, w.cap_in, in_bytes, dmalloc, dfree, "cudaMalloc (host-path input buffer)");
+    if (rc == SRFE_OK) rc = grow_pair(w.d_out, w.cap_out, out_bytes, dmalloc, dfree, "cudaMalloc (host-path output buffer)");
+    if (rc == SRFE_OK && stage_in) rc = grow_pair(w.h_in, w.cap_hin, in_bytes, hmalloc, hfree, "cudaMallocHost (input staging)");
+    if (rc == SRFE_OK && stage_out) rc = grow_pair(w.h_out, w.cap_hout, out_bytes, hmalloc, hfree, "cudaMallocHost (output staging)");
+    return rc;
+}
+
+static bool is_pageable(const void* host_ptr) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// rows of `row_bytes` from a strided source into a dense destination, split over a few host threads (one memcpy
+// stream per thread: a single core moves ~10 GB/s, the PCIe link ~50)
+static void gather_rows(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_stride_bytes) {
+    const size_t total = rows * row_bytes;
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = std::max(1u, std::min(nthr ? nthr / 2 : 1u, 6u));
+    if (total < (size_t)(4u << 20)) nthr = 1;
+    auto work = [=](size_t r0, size_t r1) {
+        if (src_stride_bytes == row_bytes) std::memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
+        else for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * row_bytes, src + r * src_stride_bytes, row_bytes);
+    };
+    if (nthr == 1) { work(0, rows); return; }
+    std::vector<std::thread> th;
+    const size_t per = (rows + nthr - 1) / nthr;
+    for (unsigned t = 1; t < nthr; ++t) {
+        const size_t r0 = std::min(rows, t * per), r1 = std::min(rows, r0 + per);
+        if (r0 < r1) th.emplace_back(work, r0, r1);
+    }
+    work(0, std::min(rows, per));
+    for (auto& t : th) t.join();
 }
 
 template <typename P>
@@ -552,29 +612,83 @@ static int run_host(int family, const void* pcm, bool i16, int64_t n_clips, int6
                     const P* p, float* out, int device, int64_t T, int64_t out_per_clip) {
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return fail(SRFE_ERR_NO_DEVICE, "no CUDA device"); }
+    if (device < 0 || device >= kMaxDevices) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
+    if (n_clips == 0) return SRFE_OK;
     SRFE_CUDA(cudaSetDevice(device));
     const size_t elem = i16 ? 2 : 4;
-    const int64_t chunk = n_clips < 2048 ? (n_clips > 0 ? n_clips : 1) : 2048;
-    HostWs* w = nullptr;
-    int rc = host_ws(device, (size_t)chunk * n_samples * elem, (size_t)chunk * out_per_clip * 4, &w);
+    const size_t row_bytes = (size_t)n_samples * elem, out_row_bytes = (size_t)out_per_clip * 4;
+    const bool stage_in = is_pageable(pcm), stage_out = is_pageable(out);
+    // pinned callers: 2048-clip chunks straight from / to their buffers; pageable callers: smaller chunks so that the
+    // host-side gather of chunk i+1 overlaps the transfer and kernel of chunk i
+    int64_t chunk = stage_in ? std::max<int64_t>(1, (int64_t)((32u << 20) / row_bytes)) : 2048;
+    if (n_clips < chunk) chunk = n_clips;
+    HostWs& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    int rc = host_ws_prepare(w, (size_t)chunk * row_bytes, (size_t)chunk * out_row_bytes, stage_in, stage_out);
+    int64_t pend_c0[2] = {-1, -1}, pend_nc[2] = {0, 0};          // staged outputs not yet copied back, per slot
+    auto drain = [&](int s) -> int {
+        if (pend_c0[s] < 0) return SRFE_OK;
+        cudaError_t ce = cudaStreamSynchronize(w.st[s]);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamSynchronize");
+        std::memcpy(out + pend_c0[s] * out_per_clip, w.h_out[s], (size_t)pend_nc[s] * out_row_bytes);
+        pend_c0[s] = -1;
+        return SRFE_OK;
+    };
     for (int64_t c0 = 0, i = 0; rc == SRFE_OK && c0 < n_clips; c0 += chunk, ++i) {
         const int64_t nc = (n_clips - c0 < chunk) ? n_clips - c0 : chunk;
         const int s = (int)(i & 1);
-        cudaError_t ce = cudaMemcpy2DAsync(w->d_in[s], (size_t)n_samples * elem, (const char*)pcm + (size_t)c0 * clip_stride * elem,
-                                           (size_t)clip_stride * elem, (size_t)n_samples * elem, (size_t)nc,
-                                           cudaMemcpyHostToDevice, w->st[s]);
+        const char* src = (const char*)pcm + (size_t)c0 * clip_stride * elem;
+        cudaError_t ce;
+        if (stage_in) {
+            // slot s was last used by chunk i-2: its H2D must be done before the staging buffer is overwritten
+            if (stage_out) rc = drain(s); else { ce = cudaStreamSynchronize(w.st[s]); if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaStreamSynchronize"); }
+            if (rc != SRFE_OK) break;
+            gather_rows((char*)w.h_in[s], src, (size_t)nc, row_bytes, (size_t)clip_stride * elem);
+            ce = cudaMemcpyAsync(w.d_in[s], w.h_in[s], (size_t)nc * row_bytes, cudaMemcpyHostToDevice, w.st[s]);
+        } else {
+            if (stage_out) { rc = drain(s); if (rc != SRFE_OK) break; }
+            ce = cudaMemcpy2DAsync(w.d_in[s], row_bytes, src, (size_t)clip_stride * elem, row_bytes, (size_t)nc,
+                                   cudaMemcpyHostToDevice, w.st[s]);
+        }
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D"); break; }
-        rc = run_device(family, w->d_in[s], i16, nc, n_samples, n_samples, p, w->d_out[s], w->st[s], T);
+        rc = run_device(family, w.d_in[s], i16, nc, n_samples, n_samples, p, w.d_out[s], w.st[s], T);
         if (rc != SRFE_OK) break;
-        ce = cudaMemcpyAsync(out + c0 * out_per_clip, w->d_out[s], (size_t)nc * out_per_clip * 4, cudaMemcpyDeviceToHost, w->st[s]);
+        float* dst = stage_out ? w.h_out[s] : out + c0 * out_per_clip;
+        ce = cudaMemcpyAsync(dst, w.d_out[s], (size_t)nc * out_row_bytes, cudaMemcpyDeviceToHost, w.st[s]);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "D2H"); break; }
+        if (stage_out) { pend_c0[s] = c0; pend_nc[s] = nc; }
     }
-    if (w) for (int i = 0; i < 2; ++i) {
-        cudaError_t ce = cudaStreamSynchronize(w->st[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (!w.st[i]) continue;
+        if (stage_out && rc == SRFE_OK) { rc = drain(i); continue; }
+        cudaError_t ce = cudaStreamSynchronize(w.st[i]);
         if (ce != cudaSuccess && rc == SRFE_OK) rc = cuda_fail(ce, "cudaStreamSynchronize");
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+static int release_host_ws() {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return SRFE_OK; }     // no device: nothing was allocated
+    for (int d = 0; d < kMaxDevices; ++d) {
+        HostWs& w = g_ws[d];
+        std::lock_guard<std::mutex> lk(w.mu);
+        if (!w.init) continue;
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+        for (int i = 0; i < 2; ++i) {
+            if (w.st[i]) { cudaStreamSynchronize(w.st[i]); cudaStreamDestroy(w.st[i]); w.st[i] = nullptr; }
+            if (w.d_in[i]) cudaFree(w.d_in[i]);
+            if (w.d_out[i]) cudaFree(w.d_out[i]);
+            if (w.h_in[i]) cudaFreeHost(w.h_in[i]);
+            if (w.h_out[i]) cudaFreeHost(w.h_out[i]);
+            w.d_in[i] = nullptr; w.d_out[i] = nullptr; w.h_in[i] = nullptr; w.h_out[i] = nullptr;
+        }
+        w.cap_in = w.cap_out = w.cap_hin = w.cap_hout = 0;
+        w.init = false;
+    }
+    cudaSetDevice(prev);
+    return SRFE_OK;
 }
 
 }  // namespace srfe
@@ -595,6 +709,13 @@ int srfe_device_count(void) {
     return n;
 }
 int64_t srfe_launch_count(void) { return g_launches.load(); }
+int srfe_release_host_workspace(void) { return release_host_ws(); }
+int srfe_set_tuning(const char* name, int value) {
+    if (!name || value < 0) return fail(SRFE_ERR_BAD_ARG, "srfe_set_tuning: name is NULL or value < 0");
+    for (int k = 0; k < TUNE_COUNT; ++k)
+        if (std::strcmp(name, kTuningNames[k]) == 0) { g_tune[k].store(value); return SRFE_OK; }
+    return fail(SRFE_ERR_BAD_ARG, std::string("srfe_set_tuning: unknown knob '") + name + "'");
+}
 
 #define SRFE_VALIDATE(p)                                            \
     if (!(p)) return fail(SRFE_ERR_BAD_ARG, "params is NULL");      \

@@ -30,6 +30,13 @@
 #include "../../include/srfe.h"
 #include "srfe_fft.cuh"
 
+// Developer switches exist only in -DSRFE_DEV builds; the shipped kernels carry no way to skip a phase.
+#ifdef SRFE_DEV
+#define SRFE_DBG(p, bit) ((p).debug & (bit))
+#else
+#define SRFE_DBG(p, bit) 0
+#endif
+
 namespace srfe {
 
 enum Family { FAM_SPEC = 0, FAM_FBANK = 1, FAM_MFCC = 2 };
@@ -44,7 +51,7 @@ struct KParams {
     int T, hop, start0;
     int cpc, n_groups;                 // clips per group, number of groups
     unsigned t_magic;                  // ceil(2^32 / T): f / T == umulhi(f, t_magic)
-    int debug;                         // developer switches (timing experiments only): 1 = skip the MFCC epilogue
+    int debug;                         // SRFE_DEV builds only (phase-skipping switches for timing experiments); ignored otherwise
     int sm_ctile;                      // coefficient tile offset (aliases the FFT scratch)
     const unsigned char* blob;         // tables, copied to shared memory once per CTA
     int blob_bytes;                    // multiple of 16
@@ -602,7 +609,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             }
         }
 
-        if (FAM == FAM_MFCC && !(p.debug & 1)) {
+        if (FAM == FAM_MFCC && !SRFE_DBG(p, 1)) {
             __shared__ float s_red[kMaxThreads / 32];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
@@ -633,7 +640,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 // (1) clamp, re-centre, fold -- in place: s[f] -> [f], d[f] -> [n/2 + f].  One item folds f and
                 //     n/2-1-f together: it reads and writes the same four slots, so no other thread's input is touched.
                 const int hq = half >> 1;
-                for (int idx = tid; idx < ((p.debug & 16) ? 0 : npairs * hq); idx += nthr) {
+                for (int idx = tid; idx < (SRFE_DBG(p, 16) ? 0 : npairs * hq); idx += nthr) {
                     const int q = idx / hq, f = idx - q * hq, g = half - 1 - f;
                     P2* row = tileP + q * TSP;
                     const P2 cm = fmeanP[q];
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                 __syncthreads();
                 // (2) the contraction
 #define SRFE_DCT(CB_, PQ_) dct_items<CB_, PQ_>(p, tileP, s_dfold, fmeanP, ctile, thr, npairs, TC, tid, nthr)
-                if (!(p.debug & 2)) switch (p.dct_cb * 4 + p.dct_pq) {
+                if (!SRFE_DBG(p, 2)) switch (p.dct_cb * 4 + p.dct_pq) {
                     case 2 * 4 + 1: SRFE_DCT(2, 1); break;   case 2 * 4 + 2: SRFE_DCT(2, 2); break;
                     case 3 * 4 + 1: SRFE_DCT(3, 1); break;   case 3 * 4 + 2: SRFE_DCT(3, 2); break;
                     case 4 * 4 + 1: SRFE_DCT(4, 1); break;   case 4 * 4 + 2: SRFE_DCT(4, 2); break;
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             const int R = (1 + p.n_deltas) * p.n_mfcc;
             float* oc = p.out + (long long)clip0 * R * p.T;
             if (p.layout == SRFE_LAYOUT_FT) {
-                const int n = (p.debug & 8) ? 0 : R * p.T;   // the clip's features are one contiguous block
+                const int n = SRFE_DBG(p, 8) ? 0 : R * p.T;   // the clip's features are one contiguous block
                 if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(oc) & 15) == 0)) {
                     const float4* c4 = reinterpret_cast<const float4*>(ctile);
                     float4* o4 = reinterpret_cast<float4*>(oc);

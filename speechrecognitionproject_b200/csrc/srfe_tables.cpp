@@ -1,6 +1,6 @@
 // srfe_tables.cpp -- host-side table builders (double precision).
 // Algorithms follow the reference call sites cited in include/srfe.h; parity with
-// the oracle's numpy tables is asserted by tests/test_tables.py (no GPU needed).
+// the oracle's numpy tables is asserted by tests/test_abi.py (no GPU needed).
 #include "srfe_tables.h"
 
 #include <algorithm>

@@ -32,7 +32,7 @@ __all__ = [
     "SpecParams", "FbankParams", "MfccParams", "PRESETS",
     "R_SPEC", "C_SPEC", "R_FBANK", "C_FBANK", "R_MFCC", "C_MFCC", "C_MFCC_D2",
     "spec", "fbank", "mfcc", "compute_spec", "filter_banks", "compute_mfcc",
-    "out_shape", "bytes_per_clip", "launch_count",
+    "out_shape", "bytes_per_clip", "launch_count", "set_tuning", "release_host_workspace",
 ]
 
 
@@ -136,6 +136,23 @@ def bytes_per_clip(params, n_samples: int = 16000) -> int:
 
 def launch_count() -> int:
     return int(_lib.lib().srfe_launch_count())
+
+
+_TUNING_KNOBS = ("warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc")
+
+
+def set_tuning(**knobs: int) -> None:
+    """Launch-shape overrides for tests and tuning sweeps (``srfe_set_tuning``; 0 = automatic).  ``set_tuning()``
+    with no arguments resets every knob.  Results never depend on them."""
+    if not knobs:
+        knobs = {k: 0 for k in _TUNING_KNOBS}
+    for k, v in knobs.items():
+        _lib.check(_lib.lib().srfe_set_tuning(k.encode(), int(v)))
+
+
+def release_host_workspace() -> None:
+    """Free the per-device staging workspaces of the host entry points (``srfe_release_host_workspace``)."""
+    _lib.check(_lib.lib().srfe_release_host_workspace())
 
 
 # ------------------------------------------------------------------------------------

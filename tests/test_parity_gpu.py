@@ -347,38 +347,40 @@ def test_int16_ingest_bit_identical(srfe_lib, corpus):
         S.mfcc(xi.to(torch.int32).cuda())
 
 
-def test_results_do_not_depend_on_launch_configuration(srfe_lib, corpus, monkeypatch):
+def test_results_do_not_depend_on_launch_configuration(srfe_lib, corpus):
     """compute-sanitizer is closed on this pool; as a race / hazard screen every family is run under several launch
-    configurations (developer overrides SRFE_WARPS / SRFE_CTAS / SRFE_CPC, and for MFCC every DCT tile shape
-    SRFE_DCT_CB x SRFE_DCT_PQ) and repeatedly: results must be bit-identical everywhere -- no arithmetic depends on the
+    configurations (srfe_set_tuning: warps / ctas / cpc, and for the classic MFCC kernel every DCT tile shape
+    dct_cb x dct_pq) and repeatedly: results must be bit-identical everywhere -- no arithmetic depends on the
     configuration (each DCT output is one ascending-f FFMA chain whatever the tile)."""
     x = torch.from_numpy(np.concatenate([corpus, corpus[:7]])).cuda()        # 31 clips: ragged last group
     cases = [(S.spec, S.R_SPEC), (S.spec, replace(S.C_SPEC, layout="tf")), (S.fbank, S.R_FBANK), (S.fbank, S.C_FBANK),
              (S.mfcc, S.R_MFCC), (S.mfcc, S.C_MFCC_D2)]
     configs = [None, (4, 2, 1), (8, 2, 4), (5, 2, 2), (9, 1, 1), (16, 1, 8), (13, 1, 2)]
-    envs = ("SRFE_WARPS", "SRFE_CTAS", "SRFE_CPC", "SRFE_DCT_CB", "SRFE_DCT_PQ")
-    for fn, p in cases:
-        for k in envs:
-            monkeypatch.delenv(k, raising=False)
-        base = fn(x, p)
-        trials = [(cfg, None) for cfg in configs]
-        if fn is S.mfcc:
-            trials += [(cfg, (cb, pq)) for cfg in (None, (5, 2, 1)) for cb in (2, 3, 4, 5, 6, 8) for pq in (1, 2)]
-        for cfg, dct in trials:
-            for k in envs:
-                monkeypatch.delenv(k, raising=False)
-            if cfg is not None:
-                monkeypatch.setenv("SRFE_WARPS", str(cfg[0])); monkeypatch.setenv("SRFE_CTAS", str(cfg[1])); monkeypatch.setenv("SRFE_CPC", str(cfg[2]))
-            if dct is not None:
-                monkeypatch.setenv("SRFE_DCT_CB", str(dct[0])); monkeypatch.setenv("SRFE_DCT_PQ", str(dct[1]))
-            try:
-                y1 = fn(x, p)
-            except RuntimeError as e:                    # a forced configuration may not fit in shared memory
-                assert "SRFE_ERR_TOO_LARGE" in str(e)
-                continue
-            for _ in range(3):
-                assert torch.equal(fn(x, p), y1), f"non-deterministic: {type(p).__name__} cfg={cfg} dct={dct}"
-            assert torch.equal(y1, base), f"configuration-dependent result: {type(p).__name__} cfg={cfg} dct={dct}"
+    try:
+        for fn, p in cases:
+            S.set_tuning()
+            if fn is S.mfcc:
+                S.set_tuning(mfcc_tc=1)                  # the classic kernel: the one these launch shapes apply to
+            base = fn(x, p)
+            trials = [(cfg, None) for cfg in configs]
+            if fn is S.mfcc:
+                trials += [(cfg, (cb, pq)) for cfg in (None, (5, 2, 1)) for cb in (2, 3, 4, 5, 6, 8) for pq in (1, 2)]
+            for cfg, dct in trials:
+                S.set_tuning(warps=0, ctas=0, cpc=0, dct_cb=0, dct_pq=0)
+                if cfg is not None:
+                    S.set_tuning(warps=cfg[0], ctas=cfg[1], cpc=cfg[2])
+                if dct is not None:
+                    S.set_tuning(dct_cb=dct[0], dct_pq=dct[1])
+                try:
+                    y1 = fn(x, p)
+                except RuntimeError as e:                    # a forced configuration may not fit in shared memory
+                    assert "SRFE_ERR_TOO_LARGE" in str(e)
+                    continue
+                for _ in range(3):
+                    assert torch.equal(fn(x, p), y1), f"non-deterministic: {type(p).__name__} cfg={cfg} dct={dct}"
+                assert torch.equal(y1, base), f"configuration-dependent result: {type(p).__name__} cfg={cfg} dct={dct}"
+    finally:
+        S.set_tuning()
 
 
 def test_thread_safety_two_host_threads(srfe_lib, corpus):

@@ -338,7 +338,8 @@ def test_full_size_model_mfcc_bgru_gpu_vs_reference_logits(srfe_lib):
             got = net(x)
             got_dev = net(x.cuda())
         assert got.is_cuda and torch.equal(got, got_dev)
-        # features differ from the CPU path by <= 1e-3 (MFCC tolerance); TF32 is off for cuDNN RNNs by default
-        np.testing.assert_allclose(got.cpu().numpy(), g["logits"], rtol=0, atol=2e-3, err_msg=which)
+        # features differ from the CPU path by <= 1e-3 (MFCC tolerance), which moves these logits by < 1e-5 (measured);
+        # TF32 is off for cuDNN RNNs by default
+        np.testing.assert_allclose(got.cpu().numpy(), g["logits"], rtol=0, atol=2e-4, err_msg=which)
     finally:
         patch.unpatch_model(mod)
