@@ -590,7 +590,7 @@ static bool is_pageable(const void* host_ptr) {
 static void gather_rows(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_stride_bytes) {
     const size_t total = rows * row_bytes;
     unsigned nthr = std::thread::hardware_concurrency();
-    nthr = std::max(1u, std::min(nthr ? nthr / 2 : 1u, 6u));
+    nthr = std::max(1u, std::min(nthr ? nthr / 2 : 1u, 8u));
     if (total < (size_t)(4u << 20)) nthr = 1;
     auto work = [=](size_t r0, size_t r1) {
         if (src_stride_bytes == row_bytes) std::memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
@@ -630,7 +630,8 @@ static int run_host(int family, const void* pcm, bool i16, int64_t n_clips, int6
         if (pend_c0[s] < 0) return SRFE_OK;
         cudaError_t ce = cudaStreamSynchronize(w.st[s]);
         if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamSynchronize");
-        std::memcpy(out + pend_c0[s] * out_per_clip, w.h_out[s], (size_t)pend_nc[s] * out_row_bytes);
+        // (a fresh pageable result buffer takes its first-touch page faults here: spread them over the copy threads)
+        gather_rows((char*)(out + pend_c0[s] * out_per_clip), (const char*)w.h_out[s], (size_t)pend_nc[s], out_row_bytes, out_row_bytes);
         pend_c0[s] = -1;
         return SRFE_OK;
     };

@@ -290,7 +290,7 @@ def _assert_checksums(net, g):
     assert list(sd.keys()) == [str(k) for k in g["keys"]]
     for k, want in zip(g["keys"], g["checksums"]):
         v = sd[str(k)].double()
-        np.testing.assert_allclose([float(v.sum()), float(v.abs().sum())], want, rtol=0, atol=0, err_msg=str(k))
+        np.testing.assert_allclose([float(v.sum()), float(v.abs().sum())], want, rtol=1e-12, atol=0, err_msg=str(k))   # sums re-associate across CPUs
 
 
 @pytest.mark.filterwarnings("ignore")
