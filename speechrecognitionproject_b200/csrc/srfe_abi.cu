@@ -19,6 +19,7 @@
 
 #include "../../include/srfe.h"
 #include "srfe_kernels.cuh"
+#include "srfe_mfcc_tc.cuh"
 #include "srfe_tables.h"
 
 namespace srfe {
@@ -49,6 +50,7 @@ struct Entry {
     int mel_ng = 0;             // ELL shape: groups and 2-bit run-length code (0 groups = not encodable)
     unsigned mel_code = 0;
     int n_bins = 0;
+    int tc_b_off = 0, tc_b_bytes = 0, tc_ne = 0, tc_no = 0;   // tcgen05 MFCC path: DCT B operand in the blob (0 bytes = not eligible)
 };
 
 struct Key {
@@ -249,6 +251,33 @@ static int build_entry(const srfe_mfcc_params& p, Entry* e) {
             e->dct_vars.push_back(v);
         }
     }
+    // tcgen05 path (srfe_mfcc_tc.cuh): the folded DCT-II rows as the MMA's B operand, [N x n/2] K-major in the no-swizzle
+    // UMMA layout (8-row x 16-byte core matrices, 128 B apart along K, (n/2)/4 * 128 B apart along N), even-k rows and
+    // odd-k rows separately, each as a TF32 "hi" copy (13 low mantissa bits cleared) and the fp32 remainder "lo".
+    if (p.n_mels % 16 == 0 && p.n_mels <= 128 && p.n_mfcc <= 128) {
+        const int half = p.n_mels / 2, ne = (p.n_mfcc + 1) / 2, no = p.n_mfcc / 2;
+        e->tc_ne = std::max(16, (ne + 15) / 16 * 16);
+        e->tc_no = std::max(16, (no + 15) / 16 * 16);
+        std::vector<float> bt((size_t)2 * (e->tc_ne + e->tc_no) * half, 0.f);
+        auto fill = [&](size_t base, int N, int par, int count) {
+            float* hi = bt.data() + base;
+            float* lo = hi + (size_t)N * half;
+            for (int j = 0; j < count; ++j)
+                for (int f = 0; f < half; ++f) {
+                    const float d = (float)dct[(size_t)(2 * j + par) * p.n_mels + f];
+                    uint32_t u; std::memcpy(&u, &d, 4); u &= 0xffffe000u;
+                    float dh; std::memcpy(&dh, &u, 4);
+                    const size_t off = ((size_t)(j / 8) * (half / 4) * 128 + (size_t)(f / 4) * 128 + (j % 8) * 16 + (f % 4) * 4) / 4;
+                    hi[off] = dh;
+                    lo[off] = d - dh;
+                }
+        };
+        fill(0, e->tc_ne, 0, ne);
+        fill((size_t)2 * e->tc_ne * half, e->tc_no, 1, no);
+        while (bb.data.size() % 128) bb.data.push_back(0);
+        e->tc_b_bytes = (int)bt.size() * 4;
+        e->tc_b_off = bb.add(bt.data(), bt.size() * 4);
+    }
     std::vector<float> dct_kf((size_t)p.n_mfcc * p.n_mels);
     for (size_t i = 0; i < dct_kf.size(); ++i) dct_kf[i] = (float)dct[i];
     return upload(e, bb, dct_kf);
@@ -293,6 +322,65 @@ static int launch_k(const KParams& kp, int dev, int grid, int threads, int smem_
     if (e != cudaSuccess) return cuda_fail(e, "srfe_kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SRFE_OK;
+}
+
+template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
+static int launch_tc(const KParams& kp, int dev, int grid, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_mfcc_tc_kernel<NFFT, JLO, JHI, NG, CODE, SAMP>;
+    static std::atomic<int> attr_set[kMaxDevices];
+    if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
+        SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int cur = attr_set[dev].load(std::memory_order_relaxed);
+        while (cur < smem_bytes && !attr_set[dev].compare_exchange_weak(cur, smem_bytes, std::memory_order_release)) {}
+    }
+    kern<<<grid, kTcThreads, smem_bytes, st>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_mfcc_tc_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SRFE_OK;
+}
+
+// Shared-memory plan of the tcgen05 MFCC kernel: [tables][DCT B operand][FFT scratch of the frame warps]
+// [ring of pair rows + dummy][frame means][coefficient tile (deltas only)][control block].  Returns false when the
+// parameter set / clip length is not eligible (the classic kernel takes it).
+static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_out) {
+    if (e->family != FAM_MFCC || e->tc_b_bytes == 0 || kp.T < 3 || kp.T > 128) return false;
+    auto up = [](int x, int a) { return (x + a - 1) / a * a; };
+    const int P = (kp.T + 1) / 2, fw = kTcThreads / 32 - kTcEpiWarps;
+    const int tmem_need = 2 * kp.n_filt + e->tc_ne + e->tc_no;
+    if (tmem_need > 512) return false;
+    int cols = 32;
+    while (cols < tmem_need) cols *= 2;
+    int off = up(e->blob_common, 128);
+    kp.tc_off_b = off;
+    off = up(off + e->tc_b_bytes, 128);
+    kp.sm_scratch = off;
+    off += 2 * fw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
+    kp.sm_tile = off;
+    const int TCs = kp.T + 2;
+    const int ctile = kp.n_deltas > 0 ? up((1 + kp.n_deltas) * kp.n_mfcc * TCs * 4, 16) : 0;
+    const int row_bytes = kp.tile_stride * 8 + 8;                      // pair row + its two means
+    const int left = di.smem_optin - off - ctile - 4 * TC_WORDS - 256;
+    int ring = std::min(2 * P, left / row_bytes - 1);
+    if (ring < P + 8) return false;
+    kp.tc_ring = ring;
+    off += (ring + 1) * kp.tile_stride * 8;
+    kp.tc_off_fmean = off;
+    off = up(off + (ring + 1) * 8, 16);
+    kp.sm_ctile = off;
+    off = up(off + ctile, 16);
+    kp.tc_off_ctrl = off;
+    off += 4 * TC_WORDS;
+    kp.blob_bytes = up(e->blob_common, 16);
+    kp.tc_b_src = e->tc_b_off;
+    kp.tc_b_bytes = e->tc_b_bytes;
+    kp.tc_ne = e->tc_ne;
+    kp.tc_no = e->tc_no;
+    kp.tc_tmem_cols = cols;
+    kp.tc_ring_magic = (unsigned)((0x100000000ULL + (unsigned long long)ring - 1) / (unsigned long long)ring);
+    kp.tc_p_magic = (unsigned)((0x100000000ULL + (unsigned long long)P - 1) / (unsigned long long)P);
+    *smem_out = up(off, 16);
+    return *smem_out <= di.smem_optin;
 }
 
 struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var, dct_pq; };
@@ -421,6 +509,32 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     DevInfo* di = nullptr;
     int rc = dev_info(&di);
     if (rc != SRFE_OK) return rc;
+    const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
+    const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
+    if (e->family == FAM_MFCC && tune(TUNE_MFCC_TC) != 1) {
+        // MFCC: the tcgen05 kernel whenever the parameter set and clip length fit it (n_mels % 16 == 0, <= 128 frames)
+        int smem_tc = 0;
+        KParams kt = kp;
+        if (plan_tc(e, kt, *di, &smem_tc)) {
+            const int grid = std::min(kt.n_clips, di->sms);
+#define SRFE_GO_TC(N, JLO, JHI, NG, CODE)                                                                        \
+    return i16 ? launch_tc<N, JLO, JHI, NG, CODE, short>(kt, di->index, grid, smem_tc, st)                       \
+               : launch_tc<N, JLO, JHI, NG, CODE, float>(kt, di->index, grid, smem_tc, st)
+            if (e->n_fft == 512) {
+                if (jlo >= 1 && jhi <= 15) {
+                    if (a400) SRFE_GO_TC(512, 1, 15, 8, 0xa400u);
+                    SRFE_GO_TC(512, 1, 15, 0, 0u);
+                }
+                SRFE_GO_TC(512, 0, 16, 0, 0u);
+            } else {
+                if (e500) SRFE_GO_TC(640, 0, 20, 8, 0xe500u);
+                SRFE_GO_TC(640, 0, 20, 0, 0u);
+            }
+#undef SRFE_GO_TC
+        } else if (tune(TUNE_MFCC_TC) == 2) {
+            return fail(SRFE_ERR_UNSUPPORTED, "mfcc_tc = 2: this parameter set / clip length does not fit the tcgen05 MFCC kernel");
+        }
+    }
     Config cfg;
     {   // the choice depends on (parameter set, frames per clip, batch size up to the point where the grid is full):
         // remember it -- small-batch callers (the reference's ensemble drivers run batch_size = 1) pay for the search once
@@ -465,8 +579,6 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     // bank / DCT get specialised kernels; everything else runs the generic ones.
     //   mel {8 groups, 0xa400}: 128 Slaney mels @ n_fft 512 and the reference's 120 HTK bands @ 512
     //   mel {8 groups, 0xe500}: 128 Slaney mels @ n_fft 640
-    const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
-    const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
 #define SRFE_GO(N, FAM, JLO, JHI, NG, CODE)                                                                      \
     return i16 ? launch_k<N, FAM, JLO, JHI, NG, CODE, short>(kp, di->index, grid, threads, smem, st)             \
                : launch_k<N, FAM, JLO, JHI, NG, CODE, float>(kp, di->index, grid, threads, smem, st)

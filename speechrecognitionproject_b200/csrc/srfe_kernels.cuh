@@ -70,6 +70,11 @@ struct KParams {
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
     int w_lo, w_hi;                    // non-zero extent of the window (host: picks the JLO / JHI instantiation)
+    // tcgen05 MFCC kernel (srfe_mfcc_tc.cuh)
+    int tc_b_src, tc_b_bytes, tc_off_b;        // DCT B operand (hi / lo, UMMA layout): offset in the global blob, bytes, shared-memory offset
+    int tc_ne, tc_no, tc_tmem_cols;            // accumulator widths (even / odd coefficients, multiples of 16), TMEM columns to allocate
+    int tc_ring, tc_off_fmean, tc_off_ctrl;    // ring capacity in pair rows, per-row frame means, control block
+    unsigned tc_ring_magic, tc_p_magic;        // ceil(2^32 / RING), ceil(2^32 / pairs per clip)
 };
 
 // --------------------------------------------------------------------------------
@@ -234,6 +239,104 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 }
 
 // --------------------------------------------------------------------------------
+// one frame PAIR of a half-warp: fetch -> pre-emphasis -> window -> packed FFT -> untangle.
+//   pa[r] / pb[r] = 4|X[k]|^2 / 4|X[M-k]|^2 of both frames for this lane's bins (k = l + 16 r for N = 512, bin640(l, r)
+//   for N = 640); returns 4|X[M/2]|^2 (meaningful on lane 0).  xb = the half-warp's exchange scratch.
+// --------------------------------------------------------------------------------
+template <int NFFT, int FAM, int JLO, int JHI, typename SAMP>
+__device__ __forceinline__ P2 pair_power(const KParams& p, const SAMP* __restrict__ clipA, int baseA, const SAMP* __restrict__ clipB,
+                                         int baseB, int l, int lane, const float* s_win, const FftTables& T, P2* xb, P2* pa, P2* pb) {
+    typedef FftGeom<NFFT> G;
+    constexpr int NJ = JHI - JLO;
+    // (holding the NEXT pair in registers was measured three ways -- fetched before the output stage, fetched
+    //  after the power values went to shared memory so that the loads fly under the mel loop, and at 168
+    //  registers / 12 warps: it spills or gains nothing; prefetch.global.L1 has no effect either.  The stall on
+    //  the first use of the samples stays at ~6 % of warp time.)
+    RawFrame<FAM, NJ> rawA, rawB;
+    fetch_frame<FAM, JLO, JHI, SAMP>(p, clipA, baseA, l, rawA);
+    fetch_frame<FAM, JLO, JHI, SAMP>(p, clipB, baseB, l, rawB);
+    C2 v[G::V];
+    window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
+    // The two planes of every exchange pass through the same slots: put / sync / get, twice.
+    fft_pass1<NFFT>(v, l, T);
+    C2 w[G::V];
+    __syncwarp();                               // the previous pair's readers are done with the tile
+    xs_put<NFFT, 0>(v, l, xb);
+    __syncwarp();
+    if (NFFT == 512) xs_get_512<0>(l, xb, w); else xs_get2_640<0>(l, xb, w);
+    __syncwarp();
+    xs_put<NFFT, 1>(v, l, xb);
+    __syncwarp();
+    if (NFFT == 512) {
+        xs_get_512<1>(l, xb, w);
+        dft16(w);                               // w[k2] = Z[l + 16 k2]
+        return fft_untangle_512_shfl(l, lane, w, T, pa, pb);
+    } else {
+        xs_get2_640<1>(l, xb, w);
+        fft_pass2_640(l, w, T);
+        __syncwarp();
+        xs_put3_640<0>(l, w, xb);
+        __syncwarp();
+        xs_get3_640<0>(l, xb, v);
+        __syncwarp();
+        xs_put3_640<1>(l, w, xb);
+        __syncwarp();
+        xs_get3_640<1>(l, xb, v);
+        fft_pass3_640(v);
+        return fft_untangle_640_shfl(l, lane, v, T, pa, pb);
+    }
+}
+
+// --------------------------------------------------------------------------------
+// sparse triangular band sums over the packed power buffer: one filter per lane and 16-filter group, uniform trip
+// count per group (ELL); emit(m, acc, guard) receives filter m's (frame A, frame B) sums.
+//   NG / CODE: compile-time bank shape (NG groups, 2 bits per group = float4 steps - 1), 0 = runtime metadata
+// --------------------------------------------------------------------------------
+template <int NG, unsigned CODE, typename Emit>
+__device__ __forceinline__ void mel_project(const P2* pbuf, const int2* g_meta, int n_fgroups, const int* f_start,
+                                            const float2* f_w2, int l, Emit emit) {
+    if (NG > 0) {
+        int off4 = 0;                       // all of this folds at compile time
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
+            const int m = 16 * i + l;
+            const P2* pq = pbuf + f_start[m];
+            const float2* wq = f_w2 + off4 * 32 + l;
+            P2 acc = bc(0.f);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                if (q4 < n4) {
+                    const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
+                    acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
+                    acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
+                    acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
+                    acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
+                }
+            }
+            off4 += n4;
+            emit(m, acc, i == NG - 1);
+        }
+    } else {
+        for (int i = 0; i < n_fgroups; ++i) {
+            const int2 gm = g_meta[i];
+            const int m = 16 * i + l;
+            const P2* pq = pbuf + f_start[m];
+            const float2* wq = f_w2 + gm.x * 32 + l;
+            P2 acc = bc(0.f);
+            for (int q4 = 0; q4 < gm.y; ++q4) {
+                const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
+                acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
+                acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
+                acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
+                acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
+            }
+            emit(m, acc, true);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------
 // folded DCT-II on the FP32 pipe (see the epilogue comment in the kernel)
 //   work item = (block of CB same-parity coefficients, PQ frame pairs); one THREAD per item, items dealt over the
 //   whole CTA, nothing is combined across lanes.  Per f the thread reads its pairs' folded values (PQ LDS.64) and its
@@ -316,9 +419,8 @@ template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename S
 __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
     typedef FftGeom<NFFT> G;
-    constexpr int NJ = JHI - JLO;
     constexpr int F = G::M + 1;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     const int HW = nthr >> 4;
@@ -371,44 +473,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             P2 pa[G::M / 32], pb[G::M / 32], pmid;
             const bool active = (it * HW + (hw & ~1)) < npairs;
             if (active) {                                   // warp-uniform: both half-warps of a warp run together
-                // (holding the NEXT pair in registers was measured three ways -- fetched before the output stage, fetched
-                //  after the power values went to shared memory so that the loads fly under the mel loop, and at 168
-                //  registers / 12 warps: it spills or gains nothing; prefetch.global.L1 has no effect either.  The stall on
-                //  the first use of the samples stays at ~6 % of warp time.)
-                RawFrame<FAM, NJ> rawA, rawB;
                 const FramePos cA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc), cB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
-                fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cA.c) * p.clip_stride, p.start0 + cA.t * p.hop, l, rawA);
-                fetch_frame<FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cB.c) * p.clip_stride, p.start0 + cB.t * p.hop, l, rawB);
-                C2 v[G::V];
-                window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
-                // The two planes of every exchange pass through the same slots: put / sync / get, twice.
-                fft_pass1<NFFT>(v, l, T);
-                C2 w[G::V];
-                __syncwarp();                               // the previous pair's readers are done with the tile
-                xs_put<NFFT, 0>(v, l, xb);
-                __syncwarp();
-                if (NFFT == 512) xs_get_512<0>(l, xb, w); else xs_get2_640<0>(l, xb, w);
-                __syncwarp();
-                xs_put<NFFT, 1>(v, l, xb);
-                __syncwarp();
-                if (NFFT == 512) {
-                    xs_get_512<1>(l, xb, w);
-                    dft16(w);                               // w[k2] = Z[l + 16 k2]
-                    pmid = fft_untangle_512_shfl(l, lane, w, T, pa, pb);
-                } else {
-                    xs_get2_640<1>(l, xb, w);
-                    fft_pass2_640(l, w, T);
-                    __syncwarp();
-                    xs_put3_640<0>(l, w, xb);
-                    __syncwarp();
-                    xs_get3_640<0>(l, xb, v);
-                    __syncwarp();
-                    xs_put3_640<1>(l, w, xb);
-                    __syncwarp();
-                    xs_get3_640<1>(l, xb, v);
-                    fft_pass3_640(v);
-                    pmid = fft_untangle_640_shfl(l, lane, v, T, pa, pb);
-                }
+                pmid = pair_power<NFFT, FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cA.c) * p.clip_stride, p.start0 + cA.t * p.hop,
+                                                              pcm + (long long)(clip0 + cB.c) * p.clip_stride, p.start0 + cB.t * p.hop,
+                                                              l, lane, s_win, T, xb, pa, pb);
 
                 // bin held in slot r of this lane (and its mirror M - k): natural stride-16 order for N = 512,
                 // the radix-4 order of bin640() for N = 640
@@ -528,45 +596,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
                             fsum = padd(fsum, mkp(da, db));
                         }
                     };
-                    if (NG > 0) {
-                        int off4 = 0;                       // all of this folds at compile time
-#pragma unroll
-                        for (int i = 0; i < NG; ++i) {
-                            const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
-                            const int m = 16 * i + l;
-                            const P2* pq = pbuf + f_start[m];
-                            const float2* wq = f_w2 + off4 * 32 + l;
-                            P2 acc = bc(0.f);
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) {
-                                if (q4 < n4) {
-                                    const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
-                                    acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
-                                    acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
-                                    acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
-                                    acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
-                                }
-                            }
-                            off4 += n4;
-                            emit(m, acc, i == NG - 1);
-                        }
-                    } else {
-                        for (int i = 0; i < p.n_fgroups; ++i) {
-                            const int2 gm = g_meta[i];
-                            const int m = 16 * i + l;
-                            const P2* pq = pbuf + f_start[m];
-                            const float2* wq = f_w2 + gm.x * 32 + l;
-                            P2 acc = bc(0.f);
-                            for (int q4 = 0; q4 < gm.y; ++q4) {
-                                const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
-                                acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
-                                acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
-                                acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
-                                acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
-                            }
-                            emit(m, acc, true);
-                        }
-                    }
+                    mel_project<NG, CODE>(pbuf, g_meta, p.n_fgroups, f_start, f_w2, l, emit);
                     if (FAM == FAM_MFCC) {                   // per-frame mean dB: centre of the DCT accumulation
 #pragma unroll
                         for (int o = 8; o > 0; o >>= 1) {
