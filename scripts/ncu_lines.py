@@ -8,13 +8,14 @@ kname = rows[0][1]
 import itertools
 def mangle(kname):
     # srfe_kernel<(int)512, (int)2, ..., (unsigned int)41984, (int)5, short> -> Itanium template-args fragment
-    args = re.search(r"srfe_kernel<(.*)>\(", kname).group(1).split(", ")
+    mk = re.search(r"(srfe_\w*kernel)<(.*)>\(", kname)
+    args = mk.group(2).split(", ")
     out = ""
     for a in args:
         m = re.match(r"\((unsigned int|int|bool)\)(\d+)", a)
         if m: out += "L" + {"int": "i", "unsigned int": "j", "bool": "b"}[m.group(1)] + m.group(2) + "E"
         else: out += {"float": "f", "short": "s"}[a]
-    return "srfe_kernelI" + out + "E"
+    return mk.group(1) + "I" + out + "E"
 mangled = mangle(kname)
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]; body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
@@ -56,7 +57,7 @@ if os.environ.get("REGIONS"):
     print("\naddress-ordered regions (sticky srfe_kernels.cuh line, merged per 10-line bucket; >= 0.3 % of samples)")
     sticky, runs = 0, []
     for r, loc in zip(body, lines):
-        if loc[0] == "srfe_kernels.cuh": sticky = loc[1]
+        if loc[0] == os.environ.get("REGION_FILE", "srfe_kernels.cuh"): sticky = loc[1]
         b = sticky // 10
         i = float(r[ci["Instructions Executed"]] or 0); s = float(r[ci["# Samples"]] or 0)
         if runs and runs[-1][0] == b: runs[-1][1] += i; runs[-1][2] += s; runs[-1][3] += 1

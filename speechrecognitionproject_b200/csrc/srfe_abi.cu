@@ -344,10 +344,10 @@ static int launch_tc(const KParams& kp, int dev, int grid, int smem_bytes, cudaS
 // [ring of pair rows + dummy][frame means][coefficient tile (deltas only)][control block].  Returns false when the
 // parameter set / clip length is not eligible (the classic kernel takes it).
 static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_out) {
-    if (e->family != FAM_MFCC || e->tc_b_bytes == 0 || kp.T < 3 || kp.T > 128) return false;
+    if (e->family != FAM_MFCC || e->tc_b_bytes == 0 || kp.T < 3 || kp.T > 4 * (32 - 2 * kp.n_deltas)) return false;
     auto up = [](int x, int a) { return (x + a - 1) / a * a; };
-    const int P = (kp.T + 1) / 2, fw = kTcThreads / 32 - kTcEpiWarps;
-    const int tmem_need = 2 * kp.n_filt + e->tc_ne + e->tc_no;
+    const int P = (kp.T + 1) / 2, nw = kTcThreads / 32;              // every warp (epilogue warps included) runs frame pairs
+    const int tmem_need = 2 * kp.n_filt + 3 * (e->tc_ne + e->tc_no);   // A operand (s / d, hi / lo) + three accumulators per parity
     if (tmem_need > 512) return false;
     int cols = 32;
     while (cols < tmem_need) cols *= 2;
@@ -355,10 +355,9 @@ static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_ou
     kp.tc_off_b = off;
     off = up(off + e->tc_b_bytes, 128);
     kp.sm_scratch = off;
-    off += 2 * fw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
+    off += 2 * nw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
     kp.sm_tile = off;
-    const int TCs = kp.T + 2;
-    const int ctile = kp.n_deltas > 0 ? up((1 + kp.n_deltas) * kp.n_mfcc * TCs * 4, 16) : 0;
+    const int ctile = 0;                                               // deltas run in registers (warp shuffles)
     const int row_bytes = kp.tile_stride * 8 + 8;                      // pair row + its two means
     const int left = di.smem_optin - off - ctile - 4 * TC_WORDS - 256;
     int ring = std::min(2 * P, left / row_bytes - 1);
@@ -511,8 +510,11 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     if (rc != SRFE_OK) return rc;
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
     const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
-    if (e->family == FAM_MFCC && tune(TUNE_MFCC_TC) != 1) {
-        // MFCC: the tcgen05 kernel whenever the parameter set and clip length fit it (n_mels % 16 == 0, <= 128 frames)
+    // MFCC: the tcgen05 kernel when the parameter set and clip length fit it (n_mels % 16 == 0, <= 128 frames, 112 with
+    // deltas) and the clip fills more than half of the 128-row MMA tile -- below that (e.g. the reference's 51-frame clips)
+    // the classic kernel measured faster (B200, 16,384 clips: R-MFCC 15.6 vs 14.4 M clips/s; C-MFCC 11.5 vs 14.9; with two
+    // deltas 9.7 vs 12.4).  srfe_set_tuning("mfcc_tc", 1 | 2) forces either.
+    if (e->family == FAM_MFCC && tune(TUNE_MFCC_TC) != 1 && (kp.T > 64 || tune(TUNE_MFCC_TC) == 2)) {
         int smem_tc = 0;
         KParams kt = kp;
         if (plan_tc(e, kt, *di, &smem_tc)) {

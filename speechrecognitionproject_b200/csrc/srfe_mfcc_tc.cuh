@@ -2,7 +2,7 @@
 //
 // One persistent 16-warp CTA per SM, warp-specialised, NO CTA-wide barrier in steady state:
 //
-//   frame warps (0 .. FW-1)      claim frame PAIRS from a shared-memory counter (a warp takes two, one per half-warp) and
+//   every warp                   (the epilogue warps only while they have nothing to finish) claims frame PAIRS from a shared-memory counter (a warp takes two, one per half-warp) and
 //                                run the packed half-warp FFT -> power -> sparse Slaney sums -> log2 of srfe_kernels.cuh;
 //                                the (frame A, frame B) mel rows go into a RING of pair rows in shared memory
 //                                (capacity ~2 clips), followed by an atomic max (clip-wide top_db reference) and an
@@ -17,21 +17,23 @@
 //        MMA      one thread: [128 frames x n/2] . [n/2 x N] for even and odd coefficients, 3 products each
 //                 (hi hi + lo hi + hi lo = fp32-grade), kind::tf32, A from TMEM, B (folded DCT-II rows, hi / lo) from
 //                 shared memory (K-major, no swizzle), accumulators in TMEM; tcgen05.commit -> mbarrier
-//        stage 2  tcgen05.ld of the thread's coefficients, + c_t sqrt(n) on c0, then either straight to global memory
-//                 (no deltas: [k][t] rows are coalesced across the warp's frames) or through a shared-memory tile for
-//                 the np.gradient passes.
+//        stage 2  tcgen05.ld of the thread's coefficients (three partial accumulators summed), + c_t sqrt(n) on c0,
+//                 np.gradient deltas through warp shuffles (each quadrant carries a halo of n_deltas frames, so time
+//                 neighbours are always lanes of the same warp), straight to global memory: [k][t] rows are coalesced
+//                 across the warp's frames.
 //
 // Parity: same arithmetic as the classic kernel up to the contraction (identical frame / mel code); the contraction's
 // 3xTF32 error is ~2^-22 relative per product on re-centred values (|x - c_t| < 30 log2 units).
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 
 #include "srfe_kernels.cuh"
 
 namespace srfe {
 
-constexpr int kTcThreads = 512;
+constexpr int kTcThreads = 512;               // 12 frame warps + 4 epilogue warps at 128 registers (16 + 4 at 96 measured: no faster)
 constexpr int kTcEpiWarps = 4;
 constexpr int kTcSlots = 4;                  // clips whose counters can be live at once (ring < 2 clips => 3 suffice)
 
@@ -55,6 +57,15 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t tc_ld1_issue(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
 // shared-memory matrix descriptor: K-major, no swizzle, core matrix = 8 rows x 16 B contiguous;
 // LBO = byte step between core matrices along K, SBO = along the row (N) dimension
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -72,7 +83,6 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
-__device__ __forceinline__ void tc_epi_bar() { asm volatile("bar.sync 1, %0;" :: "n"(32 * kTcEpiWarps) : "memory"); }
 
 template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
 __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KParams p) {
@@ -129,211 +139,231 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
     const int P = (p.T + 1) >> 1;                                                        // frame pairs per clip
     const int total = nc * P;
 
-    if (warp < FW) {
-        // ================================ frame warps =====================================================
-        P2* xb = reinterpret_cast<P2*>(smem + p.sm_scratch) + (tid >> 4) * G::SCRATCH_P2;
-        for (;;) {
-            int g0 = 0;
+    // Every warp runs the frame loop below; the four epilogue warps (FW .. FW+3, one per TMEM quadrant) first put every
+    // COMPLETE clip through the epilogue, and join the frame work only for pairs whose ring rows are free already (every
+    // clip before the one they wait for has been consumed), so an epilogue warp never waits on a resource that only it can
+    // release.
+    const bool is_epi = warp >= FW;
+    const int qd = is_epi ? warp - FW : 0;                  // TMEM quadrant == warp % 4 (FW is a multiple of 4)
+    // frame of (quadrant, lane): with deltas every quadrant carries a halo of n_deltas frames on either side (TMEM rows of
+    // two quadrants overlap in time), so that np.gradient's neighbours are always lanes of the same warp
+    const int halo = p.n_deltas, own = 32 - 2 * halo;
+    const int t = own * qd + lane - halo;                   // this thread's frame (may lie outside [0, T): clamped duplicates)
+    const int tr = min(max(t, 0), p.T - 1);
+    const bool towned = lane >= halo && lane < 32 - halo && t < p.T;
+    const int n = p.n_filt, half = n >> 1;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * qd) << 16);
+    // TMEM columns: A operand s_hi | s_lo | d_hi | d_lo (n/2 each), then 3 accumulators per parity (one per product, summed
+    // in stage 2): back-to-back MMAs into ONE accumulator serialise on the MMA pipeline latency, six chains interleave
+    const uint32_t col_sh = 0, col_sl = half, col_dh = 2 * half, col_dl = 3 * half, col_de = 4 * half, col_do = 4 * half + 3 * p.tc_ne;
+    const int R = (1 + p.n_deltas) * p.n_mfcc;
+
+    int ci = 0;                                             // epilogue warps: the next clip to finish
+#ifdef SRFE_DEV
+    long long tk_s1 = 0, tk_sync = 0, tk_mma = 0, tk_s2 = 0, tk_help = 0, tk_idle = 0, tk_mark = clock64(), tk_t0 = tk_mark;
+    int n_help = 0;
+#define SRFE_TICK(acc) do { const long long now__ = clock64(); acc += now__ - tk_mark; tk_mark = now__; } while (0)
+#else
+#define SRFE_TICK(acc) do { } while (0)
+#endif
+    P2* xb = reinterpret_cast<P2*>(smem + p.sm_scratch) + (tid >> 4) * G::SCRATCH_P2;
+    for (;;) {
+        int g0 = 0;
+        if (is_epi) {
+            bool quit = false;
+            for (;;) {
+                if (ci == nc) { quit = true; break; }
+                const int slot = ci & (kTcSlots - 1);
+                if (ctrl[TC_DONE + slot] >= P) {
+                    SRFE_TICK(tk_idle);
+                    __threadfence_block();                                        // every pair of the clip is in the ring
+                    const float gmax = tc_funkey(ctrl[TC_GMAX + slot]);
+                    const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;     // power_to_db(top_db), log2 units
+                    // ---- stage 1: ring row -> clamp, re-centre, fold, split -> TMEM A operand ----
+                    const int gp = ci * P + (tr >> 1);
+                    const int row = gp - (int)__umulhi((unsigned)gp, p.tc_ring_magic) * RING;
+                    const float* xrow = reinterpret_cast<const float*>(tileP + row * TSP) + (tr & 1);     // element m at xrow[2 m]
+                    const float cm = reinterpret_cast<const float*>(fmeanP + row)[tr & 1];
+                    const float c = fmaxf(cm, thr);                 // centre of the accumulation (classic kernel: same choice)
+                    for (int f0 = 0; f0 < half; f0 += 8) {
+                        float sh[8], sl[8], dh[8], dl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int f = f0 + j;
+                            const float a0 = fmaxf(xrow[2 * f], thr) - c, a1 = fmaxf(xrow[2 * (n - 1 - f)], thr) - c;
+                            const float s = a0 + a1, d = a0 - a1;
+                            sh[j] = __uint_as_float(__float_as_uint(s) & 0xffffe000u);       // TF32 part (kind::tf32 ignores the 13 low bits)
+                            sl[j] = s - sh[j];
+                            dh[j] = __uint_as_float(__float_as_uint(d) & 0xffffe000u);
+                            dl[j] = d - dh[j];
+                        }
+                        tc_st8(lane_base + col_sh + f0, sh);
+                        tc_st8(lane_base + col_sl + f0, sl);
+                        tc_st8(lane_base + col_dh + f0, dh);
+                        tc_st8(lane_base + col_dl + f0, dl);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    SRFE_TICK(tk_s1);
+                    int last = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        last = atomicAdd(const_cast<int*>(&ctrl[TC_S1 + slot]), 1) == kTcEpiWarps - 1;
+                    }
+                    last = __shfl_sync(0xffffffffu, last, 0);
+                    if (last) {                                     // all four quadrants are in TMEM: this warp issues the contraction
+                        if (lane == 0) {
+                            __threadfence_block();
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t sb = tc_smem(smem + p.tc_off_b);
+                            const uint32_t lbo = 128, sbo = (uint32_t)half * 32;             // (half / 4) core matrices of 128 B per 8-row group
+                            const uint32_t be_bytes = (uint32_t)p.tc_ne * half * 4, bo_bytes = (uint32_t)p.tc_no * half * 4;
+                            // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+                            const uint32_t id_e = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_ne >> 3) << 17) | ((128u >> 4) << 24);
+                            const uint32_t id_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_no >> 3) << 17) | ((128u >> 4) << 24);
+                            for (int ks = 0; ks < half / 8; ++ks) {
+#pragma unroll
+                                for (int par = 0; par < 2; ++par) {
+                                    const uint32_t b_hi = sb + (par ? 2 * be_bytes : 0), b_lo = b_hi + (par ? bo_bytes : be_bytes);
+                                    const uint32_t a_hi = tmem + (par ? col_dh : col_sh), a_lo = tmem + (par ? col_dl : col_sl);
+                                    const uint32_t nn = par ? p.tc_no : p.tc_ne, dcol = tmem + (par ? col_do : col_de), idesc = par ? id_o : id_e;
+#pragma unroll
+                                    for (int pr = 0; pr < 3; ++pr) {    // hi hi, lo hi, hi lo -> accumulators 0, 1, 2
+                                        const uint32_t a = pr == 1 ? a_lo : a_hi, b = pr == 2 ? b_lo : b_hi;
+                                        tc_mma_tf32(dcol + pr * nn, a + 8 * ks, tc_desc(b + ks * 2 * lbo, lbo, sbo), idesc, ks > 0);
+                                    }
+                                }
+                            }
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+                            // the clip's ring rows and counters are free again (nobody reads them after stage 1)
+                            ctrl[TC_S1 + slot] = 0; ctrl[TC_DONE + slot] = 0; ctrl[TC_GMAX + slot] = (int)0x80000000;
+                            __threadfence_block();
+                            ctrl[TC_CONSUMED] = ci + 1;
+                        }
+                        __syncwarp();
+                    }
+                    // ---- stage 2: coefficients of this thread's frame, deltas through warp shuffles, straight to global ----
+                    SRFE_TICK(tk_sync);
+                    tc_mbar_wait(bar, (uint32_t)(ci & 1));
+                    SRFE_TICK(tk_mma);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    float* oc = p.out + (long long)((int)blockIdx.x + ci * (int)gridDim.x) * R * p.T;
+                    // element (row r = d n_mfcc + k, frame t): FT -> oc[r T + t] (coalesced across the warp's frames), TF -> oc[t R + r]
+                    const int st_r = p.layout == SRFE_LAYOUT_FT ? p.T : 1;                       // stride between rows
+                    float* ot = oc + (p.layout == SRFE_LAYOUT_FT ? t : t * R);
+                    // A deliberately ROLLED loop, one even and one odd coefficient per trip: the epilogue's code is cold every time
+                    // it runs (the frame warps stream ~100 KB of unrolled FFT code through the instruction caches in between),
+                    // and an unrolled version of this stage measured 5-8x slower on instruction fetch alone.
+                    const int st_d = p.n_mfcc * st_r;
+                    const uint32_t de = lane_base + col_de, dox = lane_base + col_do;
+                    const float c0fix = c * p.dct_row0_sum;                                      // put the frame's centre back on c0
+#pragma unroll 1
+                    for (int j = 0; 2 * j < p.n_mfcc; ++j) {      // (4 + 4 coefficients per trip measured slower: more code to fetch)
+                        const uint32_t e0 = tc_ld1_issue(de + j), e1 = tc_ld1_issue(de + p.tc_ne + j), e2 = tc_ld1_issue(de + 2 * p.tc_ne + j);
+                        const uint32_t o0 = tc_ld1_issue(dox + j), o1 = tc_ld1_issue(dox + p.tc_no + j), o2 = tc_ld1_issue(dox + 2 * p.tc_no + j);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float ve = (__uint_as_float(e0) + __uint_as_float(e1)) + __uint_as_float(e2);
+                        float vo = (__uint_as_float(o0) + __uint_as_float(o1)) + __uint_as_float(o2);
+                        if (j == 0) ve += c0fix;
+                        const bool odd_ok = 2 * j + 1 < p.n_mfcc;
+                        float* o = ot + 2 * j * st_r;                                           // rows k = 2 j and 2 j + 1
+                        if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
+#pragma unroll 1
+                        for (int d = 1; d <= p.n_deltas; ++d) {
+                            // np.gradient along time (unit spacing, edge_order 1): neighbours are lanes of this warp
+                            const float ue = __shfl_down_sync(0xffffffffu, ve, 1), le = __shfl_up_sync(0xffffffffu, ve, 1);
+                            const float uo = __shfl_down_sync(0xffffffffu, vo, 1), lo = __shfl_up_sync(0xffffffffu, vo, 1);
+                            ve = t <= 0 ? ue - ve : (t >= p.T - 1 ? ve - le : 0.5f * (ue - le));
+                            vo = t <= 0 ? uo - vo : (t >= p.T - 1 ? vo - lo : 0.5f * (uo - lo));
+                            o += st_d;
+                            if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    SRFE_TICK(tk_s2);
+                    ++ci;
+                    continue;
+                }
+                int got = 0;
+                if (lane == 0) {
+                    const int nx = ctrl[TC_NEXT];
+                    if (nx + 2 <= min(ci * P + RING, total)) { got = atomicCAS(const_cast<int*>(&ctrl[TC_NEXT]), nx, nx + 2) == nx; g0 = nx; }
+                }
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got) break;
+                __nanosleep(100);
+            }
+            SRFE_TICK(tk_idle);
+#ifdef SRFE_DEV
+            if (quit && blockIdx.x == 0 && lane == 0)
+                printf("epi warp %d: clips %d cycles/clip: total %lld idle %lld stage1 %lld sync+issue %lld mma-wait %lld stage2 %lld help %lld (%d iterations)\n",
+                       qd, nc, (clock64() - tk_t0) / nc, tk_idle / nc, tk_s1 / nc, tk_sync / nc, tk_mma / nc, tk_s2 / nc, tk_help / nc, n_help);
+            if (!quit) ++n_help;
+#endif
+            if (quit) break;
+            g0 = __shfl_sync(0xffffffffu, g0, 0);
+        } else {
             if (lane == 0) g0 = atomicAdd(const_cast<int*>(&ctrl[TC_NEXT]), 2);
             g0 = __shfl_sync(0xffffffffu, g0, 0);
             if (g0 >= total) break;
-            const int g = g0 + (lane >> 4);
-            const bool valid = g < total;                   // an odd stream ends with a half-warp that recomputes the last pair, no side effects
-            const int gg = valid ? g : total - 1;
-            const int ci = (int)__umulhi((unsigned)gg, p.tc_p_magic);     // gg / P
-            const int q = gg - ci * P;
-            const SAMP* clip = pcm + (long long)((int)blockIdx.x + ci * (int)gridDim.x) * p.clip_stride;
-            const int fA = 2 * q, fB = min(2 * q + 1, p.T - 1);         // odd T: the last pair's second frame repeats the last frame
-            P2 pa[G::M / 32], pb[G::M / 32];
-            const P2 pmid = pair_power<NFFT, FAM, JLO, JHI, SAMP>(p, clip, p.start0 + fA * p.hop, clip, p.start0 + fB * p.hop,
-                                                                  l, lane, s_win, T, xb, pa, pb);
-            P2* pbuf = xb;
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < G::M / 32; ++r) {
-                const int k = NFFT == 512 ? l + 16 * r : bin640(l, r);
-                pbuf[k] = pa[r];
-                pbuf[G::M - k] = pb[r];
-            }
-            if (l == 0) pbuf[G::M / 2] = pmid;
-            __syncwarp();
-            // the ring row of this pair: free once the clip that last used it has been through stage 1
-            const int row = valid ? gg - (int)__umulhi((unsigned)gg, p.tc_ring_magic) * RING : RING;       // RING = dummy row
-            if (valid && gg >= RING) {
-                const int need = (int)__umulhi((unsigned)(gg - RING), p.tc_p_magic);                     // clip of pair gg - RING
-                while (ctrl[TC_CONSUMED] <= need) __nanosleep(64);
-                __threadfence_block();
-            }
-            P2* prow = tileP + row * TSP;
-            P2 fsum = bc(0.f);
-            float run_max = -CUDART_INF_F;
-            auto emit = [&](int m, const P2& acc, bool guard) {
-                if (guard && m >= p.n_filt) return;
-                // log2 units: 10 log10(2) lives in the DCT operand and in top_db (host, double precision)
-                const float da = lg2_ftz(fmaxf(acc.lo, p.amin));
-                const float db = lg2_ftz(fmaxf(acc.hi, p.amin));
-                prow[m] = mkp(da, db);
-                run_max = fmaxf(run_max, fmaxf(da, db));
-                fsum = padd(fsum, mkp(da, db));
-            };
-            mel_project<NG, CODE>(pbuf, g_meta, p.n_fgroups, f_start, f_w2, l, emit);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                fsum.lo += __shfl_xor_sync(0xffffffffu, fsum.lo, o);
-                fsum.hi += __shfl_xor_sync(0xffffffffu, fsum.hi, o);
-                run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
-            }
-            if (l == 0) fmeanP[row] = pmul(fsum, bc(1.f / (float)p.n_filt));
-            __syncwarp();                                   // the half-warp's row is complete (and pbuf free for the next pair)
-            if (valid && l == 0) {
-                atomicMax(const_cast<int*>(&ctrl[TC_GMAX + (ci & (kTcSlots - 1))]), tc_fkey(run_max));
-                __threadfence_block();                      // row, mean and max before the count
-                atomicAdd(const_cast<int*>(&ctrl[TC_DONE + (ci & (kTcSlots - 1))]), 1);
-            }
         }
-    } else {
-        // ================================ epilogue warps ==================================================
-        const int qd = warp - FW;                           // TMEM quadrant == warp % 4 (FW is a multiple of 4)
-        const int t = 32 * qd + lane;                       // this thread's frame
-        const bool tvalid = t < p.T;
-        const int n = p.n_filt, half = n >> 1;
-        const uint32_t lane_base = tmem + ((uint32_t)(32 * qd) << 16);
-        const uint32_t col_sh = 0, col_sl = half, col_dh = 2 * half, col_dl = 3 * half, col_de = 4 * half, col_do = 4 * half + p.tc_ne;
-        const int R = (1 + p.n_deltas) * p.n_mfcc;
-        const int TC = (p.layout == SRFE_LAYOUT_FT) ? p.T : p.T + 1 + (p.T & 1);
-        float* ctile = reinterpret_cast<float*>(smem + p.sm_ctile);
-        const int etid = tid - 32 * FW, ewarp = qd;
-
-        for (int ci = 0; ci < nc; ++ci) {
-            const int slot = ci & (kTcSlots - 1);
-            while (ctrl[TC_DONE + slot] < P) __nanosleep(64);             // every pair of the clip is in the ring
+        const int g = g0 + (lane >> 4);
+        const bool valid = g < total;                   // an odd stream ends with a half-warp that recomputes the last pair, no side effects
+        const int gg = valid ? g : total - 1;
+        const int pc = (int)__umulhi((unsigned)gg, p.tc_p_magic);     // the pair's clip: gg / P
+        const int q = gg - pc * P;
+        const SAMP* clip = pcm + (long long)((int)blockIdx.x + pc * (int)gridDim.x) * p.clip_stride;
+        const int fA = 2 * q, fB = min(2 * q + 1, p.T - 1);         // odd T: the last pair's second frame repeats the last frame
+        P2 pa[G::M / 32], pb[G::M / 32];
+        const P2 pmid = pair_power<NFFT, FAM, JLO, JHI, SAMP>(p, clip, p.start0 + fA * p.hop, clip, p.start0 + fB * p.hop,
+                                                              l, lane, s_win, T, xb, pa, pb);
+        P2* pbuf = xb;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < G::M / 32; ++r) {
+            const int k = NFFT == 512 ? l + 16 * r : bin640(l, r);
+            pbuf[k] = pa[r];
+            pbuf[G::M - k] = pb[r];
+        }
+        if (l == 0) pbuf[G::M / 2] = pmid;
+        __syncwarp();
+        // the ring row of this pair: free once the clip that last used it has been through stage 1
+        const int row = valid ? gg - (int)__umulhi((unsigned)gg, p.tc_ring_magic) * RING : RING;       // RING = dummy row
+        if (valid && gg >= RING) {
+            const int need = (int)__umulhi((unsigned)(gg - RING), p.tc_p_magic);                     // clip of pair gg - RING
+            while (ctrl[TC_CONSUMED] <= need) __nanosleep(64);
             __threadfence_block();
-            const float gmax = tc_funkey(ctrl[TC_GMAX + slot]);
-            const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;     // power_to_db(top_db), log2 units
-            // ---- stage 1: ring row -> clamp, re-centre, fold, split -> TMEM A operand ----
-            const int gp = ci * P + (t >> 1);
-            const int row = gp - (int)__umulhi((unsigned)gp, p.tc_ring_magic) * RING;
-            const float* xrow = reinterpret_cast<const float*>(tileP + row * TSP) + (t & 1);      // element m at xrow[2 m]
-            const float cm = reinterpret_cast<const float*>(fmeanP + row)[t & 1];
-            const float c = fmaxf(cm, thr);                 // centre of the accumulation (classic kernel: same choice)
-            for (int f0 = 0; f0 < half; f0 += 8) {
-                float sh[8], sl[8], dh[8], dl[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int f = f0 + j;
-                    const float a0 = fmaxf(xrow[2 * f], thr) - c, a1 = fmaxf(xrow[2 * (n - 1 - f)], thr) - c;
-                    const float s = tvalid ? a0 + a1 : 0.f, d = tvalid ? a0 - a1 : 0.f;
-                    sh[j] = __uint_as_float(__float_as_uint(s) & 0xffffe000u);       // TF32 part (kind::tf32 ignores the 13 low bits)
-                    sl[j] = s - sh[j];
-                    dh[j] = __uint_as_float(__float_as_uint(d) & 0xffffe000u);
-                    dl[j] = d - dh[j];
-                }
-                tc_st8(lane_base + col_sh + f0, sh);
-                tc_st8(lane_base + col_sl + f0, sl);
-                tc_st8(lane_base + col_dh + f0, dh);
-                tc_st8(lane_base + col_dl + f0, dl);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) {
-                __threadfence_block();
-                last = atomicAdd(const_cast<int*>(&ctrl[TC_S1 + slot]), 1) == kTcEpiWarps - 1;
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {                                     // all four quadrants are in TMEM: this warp issues the contraction
-                if (lane == 0) {
-                    __threadfence_block();
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sb = tc_smem(smem + p.tc_off_b);
-                    const uint32_t lbo = 128, sbo = (uint32_t)half * 32;             // (half / 4) core matrices of 128 B per 8-row group
-                    const uint32_t be_bytes = (uint32_t)p.tc_ne * half * 4, bo_bytes = (uint32_t)p.tc_no * half * 4;
-                    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-                    const uint32_t id_e = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_ne >> 3) << 17) | ((128u >> 4) << 24);
-                    const uint32_t id_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_no >> 3) << 17) | ((128u >> 4) << 24);
-                    for (int par = 0; par < 2; ++par) {
-                        const uint32_t b_hi = sb + (par ? 2 * be_bytes : 0), b_lo = b_hi + (par ? bo_bytes : be_bytes);
-                        const uint32_t a_hi = tmem + (par ? col_dh : col_sh), a_lo = tmem + (par ? col_dl : col_sl);
-                        const uint32_t dcol = tmem + (par ? col_do : col_de), idesc = par ? id_o : id_e;
-                        uint32_t acc = 0;
-                        for (int pr = 0; pr < 3; ++pr) {    // hi hi + lo hi + hi lo
-                            const uint32_t a = pr == 1 ? a_lo : a_hi, b = pr == 2 ? b_lo : b_hi;
-                            for (int ks = 0; ks < half / 8; ++ks) {
-                                tc_mma_tf32(dcol, a + 8 * ks, tc_desc(b + ks * 2 * lbo, lbo, sbo), idesc, acc);
-                                acc = 1;
-                            }
-                        }
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-                    // the clip's ring rows and counters are free again (nobody reads them after stage 1)
-                    ctrl[TC_S1 + slot] = 0; ctrl[TC_DONE + slot] = 0; ctrl[TC_GMAX + slot] = (int)0x80000000;
-                    __threadfence_block();
-                    ctrl[TC_CONSUMED] = ci + 1;
-                }
-                __syncwarp();
-            }
-            // ---- stage 2: coefficients of this thread's frame ----
-            tc_mbar_wait(bar, (uint32_t)(ci & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float* oc = p.out + (long long)((int)blockIdx.x + ci * (int)gridDim.x) * R * p.T;
-            const bool direct = p.n_deltas == 0;
-            for (int par = 0; par < 2; ++par) {
-                const int nk = par ? (p.n_mfcc >> 1) : ((p.n_mfcc + 1) >> 1);
-                for (int j0 = 0; j0 < nk; j0 += 8) {
-                    float v[8];
-                    tc_ld8(lane_base + (par ? col_do : col_de) + j0, v);
-                    if (par == 0 && j0 == 0) v[0] = fmaf(c, p.dct_row0_sum, v[0]);   // put the frame's centre back on c0
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = 2 * (j0 + j) + par;
-                        if (j0 + j < nk && tvalid) {
-                            if (!direct) ctile[k * TC + t] = v[j];
-                            else if (p.layout == SRFE_LAYOUT_FT) oc[k * p.T + t] = v[j];   // coalesced across the warp's frames
-                            else oc[t * R + k] = v[j];
-                        }
-                    }
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (!direct) {
-                // np.gradient along time (unit spacing, edge_order 1), n_deltas times, then the coalesced copy-out:
-                // the four epilogue warps together (named barrier 1)
-                tc_epi_bar();
-                for (int d = 1; d <= p.n_deltas; ++d) {
-                    const float* src = ctile + (d - 1) * p.n_mfcc * TC;
-                    float* dst = ctile + d * p.n_mfcc * TC;
-                    for (int k = ewarp; k < p.n_mfcc; k += kTcEpiWarps) {
-                        const float* sr = src + k * TC;
-                        for (int tt = lane; tt < p.T; tt += 32) {
-                            float gr;
-                            if (tt == 0) gr = sr[1] - sr[0];
-                            else if (tt == p.T - 1) gr = sr[tt] - sr[tt - 1];
-                            else gr = 0.5f * (sr[tt + 1] - sr[tt - 1]);
-                            dst[k * TC + tt] = gr;
-                        }
-                    }
-                    tc_epi_bar();
-                }
-                if (p.layout == SRFE_LAYOUT_FT) {
-                    const int nn = R * p.T;
-                    if (((nn & 3) == 0) && ((reinterpret_cast<uintptr_t>(oc) & 15) == 0)) {
-                        const float4* c4 = reinterpret_cast<const float4*>(ctile);
-                        float4* o4 = reinterpret_cast<float4*>(oc);
-                        for (int i = etid; i < (nn >> 2); i += 32 * kTcEpiWarps) o4[i] = c4[i];
-                    } else {
-                        for (int i = etid; i < nn; i += 32 * kTcEpiWarps) oc[i] = ctile[i];
-                    }
-                } else {
-                    for (int tt = ewarp; tt < p.T; tt += kTcEpiWarps) {
-                        float* orow = oc + tt * R;
-                        const float* ccol = ctile + tt;
-                        for (int r = lane; r < R; r += 32) orow[r] = ccol[r * TC];
-                    }
-                }
-                tc_epi_bar();                               // the tile is rewritten by the next clip's stage 2
-            }
         }
+        P2* prow = tileP + row * TSP;
+        P2 fsum = bc(0.f);
+        float run_max = -CUDART_INF_F;
+        auto emit = [&](int m, const P2& acc, bool guard) {
+            if (guard && m >= p.n_filt) return;
+            // log2 units: 10 log10(2) lives in the DCT operand and in top_db (host, double precision)
+            const float da = lg2_ftz(fmaxf(acc.lo, p.amin));
+            const float db = lg2_ftz(fmaxf(acc.hi, p.amin));
+            prow[m] = mkp(da, db);
+            run_max = fmaxf(run_max, fmaxf(da, db));
+            fsum = padd(fsum, mkp(da, db));
+        };
+        mel_project<NG, CODE>(pbuf, g_meta, p.n_fgroups, f_start, f_w2, l, emit);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            fsum.lo += __shfl_xor_sync(0xffffffffu, fsum.lo, o);
+            fsum.hi += __shfl_xor_sync(0xffffffffu, fsum.hi, o);
+            run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+        }
+        if (l == 0) fmeanP[row] = pmul(fsum, bc(1.f / (float)p.n_filt));
+        __syncwarp();                                   // the half-warp's row is complete (and pbuf free for the next pair)
+        if (valid && l == 0) {
+            atomicMax(const_cast<int*>(&ctrl[TC_GMAX + (pc & (kTcSlots - 1))]), tc_fkey(run_max));
+            __threadfence_block();                      // row, mean and max before the count
+            atomicAdd(const_cast<int*>(&ctrl[TC_DONE + (pc & (kTcSlots - 1))]), 1);
+        }
+#ifdef SRFE_DEV
+        if (is_epi) SRFE_TICK(tk_help);
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

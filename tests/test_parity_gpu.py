@@ -501,3 +501,78 @@ def test_cuda_graph_capture_and_replay(srfe_lib, corpus):
     torch.cuda.synchronize()
     for o, w in zip(outs, want):
         assert torch.equal(o, w.flip(0))
+
+
+# ---------------------------------------------------------------- tcgen05 MFCC kernel ----
+TC_CASES = [
+    ("C-MFCC", {}), ("C-MFCC", {"layout": "tf"}), ("C-MFCC-D2", {}), ("C-MFCC-D2", {"layout": "tf"}),
+    ("R-MFCC", {}), ("R-MFCC", {"layout": "tf"}), ("R-MFCC", {"n_deltas": 1}), ("R-MFCC", {"n_deltas": 0, "n_mfcc": 20}),
+    ("C-MFCC", {"n_mels": 80, "n_mfcc": 13, "n_deltas": 2}), ("C-MFCC", {"n_mels": 64, "n_mfcc": 33, "top_db": None}),
+    ("C-MFCC", {"n_mels": 32, "n_mfcc": 12, "n_deltas": 1, "layout": "tf"}), ("C-MFCC", {"n_mels": 128, "n_mfcc": 1}),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(TC_CASES)))
+def test_mfcc_tensor_core_kernel_vs_classic_and_oracle(srfe_lib, idx):
+    """srfe_mfcc_tc_kernel (DCT-II as 3xTF32 tcgen05 MMAs, accumulators in TMEM) against the classic CUDA-core kernel and
+    the float64 oracle: every preset, both layouts, 0 / 1 / 2 deltas, odd coefficient counts, batch sizes that leave
+    CTAs with 1, 2 and 3 clips, int16 ingest."""
+    name, over = TC_CASES[idx]
+    p = replace(S.PRESETS[name], **over)
+    x = oracle.synthetic_corpus(333, config_index=9)
+    x[5] = 0.0                                               # digital silence: amin floor, c0 only
+    x[6, 8000:] = 0.0                                        # half-silent: the top_db clamp bites
+    xd = torch.from_numpy(x).cuda()
+    try:
+        for n in (1, 7, 148, 149, 333):
+            S.set_tuning(mfcc_tc=2)
+            tc = S.mfcc(xd[:n], p)
+            tc2 = S.mfcc(xd[:n], p)
+            S.set_tuning(mfcc_tc=1)
+            classic = S.mfcc(xd[:n], p)
+            assert torch.equal(tc, tc2), "tcgen05 kernel is not deterministic"
+            assert float((tc - classic).abs().max()) <= 2e-4, (name, over, n)
+        S.set_tuning(mfcc_tc=2)
+        got = S.mfcc(xd[:12], p).cpu().numpy()
+        truth = H.oracle_batch(oracle.mfcc_truth, x[:12], H.to_oracle_params(p))     # the oracle is [rows, frames]
+        if p.layout == "tf":
+            truth = truth.transpose(0, 2, 1)
+        H.check_mfcc(got, truth, f"tc {name} {over}")
+        got16 = S.mfcc(xd[:12].to(torch.int16), p).cpu().numpy()
+        np.testing.assert_array_equal(got16, got)
+    finally:
+        S.set_tuning()
+
+
+def test_mfcc_tensor_core_kernel_limits(srfe_lib):
+    """128 frames without deltas, 112 with two (each TMEM quadrant carries a halo of n_deltas frames); beyond that the
+    tcgen05 kernel refuses (mfcc_tc = 2) and the default dispatch uses the classic kernel -- same results either way."""
+    base = replace(S.C_MFCC, hop=160)
+    try:
+        for n_deltas, frames_ok in ((0, 128), (2, 112)):
+            p = replace(base, n_deltas=n_deltas)
+            for T, ok in ((frames_ok, True), (frames_ok + 1, False)):
+                x = torch.from_numpy(oracle.synthetic_corpus(5, config_index=10, n_samples=160 * (T - 1) + 40)).cuda()
+                assert S.out_shape(p, x.size(1))[1] == T
+                S.set_tuning(mfcc_tc=1)
+                classic = S.mfcc(x, p)
+                S.set_tuning(mfcc_tc=2)
+                if ok:
+                    assert float((S.mfcc(x, p) - classic).abs().max()) <= 2e-4
+                else:
+                    with pytest.raises(RuntimeError, match="SRFE_ERR_UNSUPPORTED"):
+                        S.mfcc(x, p)
+                S.set_tuning()
+                assert float((S.mfcc(x, p) - classic).abs().max()) <= 2e-4
+        # parameter sets it cannot take (n_mels not a multiple of 16) go to the classic kernel silently, refuse when forced
+        p = replace(S.C_MFCC, n_mels=40, n_mfcc=13)
+        x = torch.from_numpy(oracle.synthetic_corpus(3, config_index=10)).cuda()
+        S.set_tuning()
+        y = S.mfcc(x, p)
+        S.set_tuning(mfcc_tc=2)
+        with pytest.raises(RuntimeError, match="SRFE_ERR_UNSUPPORTED"):
+            S.mfcc(x, p)
+        S.set_tuning(mfcc_tc=1)
+        assert torch.equal(S.mfcc(x, p), y)
+    finally:
+        S.set_tuning()
