@@ -83,6 +83,10 @@ typedef struct srfe_fbank_params {
     int32_t n_fft;               /* 512 (or 640) ; frame_len <= n_fft */
     float   preemph;             /* 0.97 */
     int32_t nfilt;               /* 120 (reference), 40 (BASELINE cfg2) */
+    float   vtlp_alpha;          /* 0 = off.  Vocal-tract-length perturbation of the filter centre frequencies before they
+                                  * are floored to bins (legacy/model_8/dataset_top.py:251-252; alpha ~ U(0.9, 1.1) there):
+                                  * hz < 4800 min(alpha,1)/alpha -> hz alpha, else mapped linearly onto the rest up to
+                                  * fs/2.  One alpha per call: the table is cached per (device, parameter set). */
 } srfe_fbank_params;
 
 /* MFCC + deltas, model_mfcc_bgru.py:13-16 with librosa-0.6 semantics:
@@ -168,6 +172,38 @@ int srfe_fbank_host_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, 
                         const srfe_fbank_params* p, float* out, int device);
 int srfe_mfcc_host_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                         const srfe_mfcc_params* p, float* out, int device);
+
+/* ---- on-device augmentation + silence synthesis -------------- */
+/* What the reference's Dataset does per clip on the host with global random state -- generate_silence_sample
+ * (dataset.py:148-161), add_noise_uniform (:185-191), add_noise_snr (:163-183), time_stretching (:193-202) and the band
+ * selection of __getitem__ (:107-116) -- as ONE launch over a batch of int16 clips that stays on the device and feeds the
+ * front end on the same stream.  Randomness is a counter-based contract: Philox4x32-10, key = seed, counter = (global clip
+ * index = first_clip_index + row, draw block); the draw layout is in oracle/augment.py, whose numpy restatement this
+ * kernel matches bit for bit.  A clip takes the op whose band [lo, hi) contains its uniform draw; the reference's pitch-shift
+ * and speed-tune bands (librosa / cv2 resampling) are host-only: such clips are copied through and flagged. */
+typedef enum srfe_augment_op {
+    SRFE_AUG_NONE = 0, SRFE_AUG_SHIFT = 1, SRFE_AUG_NOISE_UNIFORM = 2, SRFE_AUG_NOISE_SNR = 3,
+    SRFE_AUG_SILENCE_ZERO = 4, SRFE_AUG_SILENCE_NOISE = 5, SRFE_AUG_HOST_PITCH = 6, SRFE_AUG_HOST_SPEED = 7
+} srfe_augment_op;
+
+typedef struct srfe_augment_params {
+    uint64_t seed;
+    float shift_lo, shift_hi;    /* time shift band          (dataset.py:112-113: 0.4, 0.6) */
+    float noise_lo, noise_hi;    /* add_noise_uniform band   (dataset.py:114-115: 0.6, 0.8) */
+    float snr_lo, snr_hi;        /* add_noise_snr band       (never called by __getitem__: 0, 0 = off) */
+    float pitch_lo, pitch_hi;    /* host-only bands, reported in op_out (0, 0.2) / (0.2, 0.4) */
+    float speed_lo, speed_hi;
+    int32_t shift_range;         /* 4800 */
+    float noise_upper;           /* 0.1 */
+} srfe_augment_params;
+
+/* pcm: DEVICE int16 [n_clips][clip_stride]; kind: DEVICE int8 per clip (0 = clip, 1 = silence of zeros, 2 = silence from a
+ * noise slice) or NULL; noise_bank: DEVICE int16, the background files back to back; noise_offsets: DEVICE int64
+ * [n_noise_files + 1] (every file at least n_samples long); out: DEVICE float32 [n_clips][n_samples] (dataset.py:117);
+ * op_out: DEVICE int8 [n_clips] (srfe_augment_op) or NULL. */
+int srfe_augment_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const int8_t* kind,
+                     int64_t first_clip_index, const int16_t* noise_bank, const int64_t* noise_offsets, int32_t n_noise_files,
+                     const srfe_augment_params* p, float* out, int8_t* op_out, void* cuda_stream);
 
 /* frees the host entry points' per-device workspaces (streams, device buffers, pinned staging); they are re-created on
  * the next host call.  Returns SRFE_OK. */

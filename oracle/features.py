@@ -48,6 +48,7 @@ class FbankParams:
     nfft: int = 512             # (:41)
     preemph: float = 0.97       # (:19)
     nfilt: int = 120            # (:45)
+    vtlp_alpha: float = 0.0     # 0 = off; legacy/model_8/dataset_top.py:251-252 (alpha ~ U(0.9, 1.1) there)
 
 
 @dataclass(frozen=True)
@@ -180,6 +181,11 @@ def htk_floor_filterbank(p: FbankParams = R_FBANK) -> np.ndarray:
     high = 2595.0 * np.log10(1.0 + (p.fs / 2.0) / 700.0)            # :47
     mel_points = np.linspace(0.0, high, p.nfilt + 2)                 # :48
     hz_points = 700.0 * (10.0 ** (mel_points / 2595.0) - 1.0)        # :49
+    if p.vtlp_alpha:                                                 # legacy/model_8/dataset_top.py:251-252, 8000 -> fs/2
+        a, nyq = float(np.float32(p.vtlp_alpha)), p.fs / 2.0
+        m1 = min(a, 1.0)
+        hz_points = np.array([h * a if h < (4800 * m1 / a) else nyq - ((nyq - 4800 * m1) / (nyq - 4800 * (m1 / a))) * (nyq - h)
+                              for h in hz_points])
     bins = np.floor((p.nfft + 1) * hz_points / p.fs)                 # :50
     fb = np.zeros((p.nfilt, p.nfft // 2 + 1))                        # :51
     for m in range(1, p.nfilt + 1):                                  # :52

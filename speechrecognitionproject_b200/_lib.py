@@ -25,13 +25,20 @@ class SpecParamsC(C.Structure):
 
 class FbankParamsC(C.Structure):
     _fields_ = [("sample_rate", C.c_int32), ("frame_len", C.c_int32), ("frame_step", C.c_int32),
-                ("n_fft", C.c_int32), ("preemph", C.c_float), ("nfilt", C.c_int32)]
+                ("n_fft", C.c_int32), ("preemph", C.c_float), ("nfilt", C.c_int32), ("vtlp_alpha", C.c_float)]
 
 
 class MfccParamsC(C.Structure):
     _fields_ = [("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32),
                 ("n_mels", C.c_int32), ("fmin", C.c_float), ("fmax", C.c_float), ("n_mfcc", C.c_int32),
                 ("n_deltas", C.c_int32), ("top_db", C.c_float), ("amin", C.c_float), ("layout", C.c_int32)]
+
+
+class AugmentParamsC(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("shift_lo", C.c_float), ("shift_hi", C.c_float), ("noise_lo", C.c_float),
+                ("noise_hi", C.c_float), ("snr_lo", C.c_float), ("snr_hi", C.c_float), ("pitch_lo", C.c_float),
+                ("pitch_hi", C.c_float), ("speed_lo", C.c_float), ("speed_hi", C.c_float), ("shift_range", C.c_int32),
+                ("noise_upper", C.c_float)]
 
 
 # every symbol include/srfe.h declares: name -> (restype, argtypes)
@@ -43,6 +50,7 @@ SYMBOLS = {
     "srfe_device_count": (_i32, []),
     "srfe_launch_count": (_i64, []),
     "srfe_release_host_workspace": (_i32, []),
+    "srfe_augment_i16": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, C.POINTER(AugmentParamsC), _vp, _vp, _vp]),
     "srfe_set_tuning": (_i32, [C.c_char_p, _i32]),
     "srfe_spec_out_shape": (_i64, [C.POINTER(SpecParamsC), _i64, _SHAPE]),
     "srfe_fbank_out_shape": (_i64, [C.POINTER(FbankParamsC), _i64, _SHAPE]),

@@ -20,6 +20,7 @@
 #include "../../include/srfe.h"
 #include "srfe_kernels.cuh"
 #include "srfe_mfcc_tc.cuh"
+#include "srfe_augment.cuh"
 #include "srfe_tables.h"
 
 namespace srfe {
@@ -825,6 +826,37 @@ int srfe_device_count(void) {
 }
 int64_t srfe_launch_count(void) { return g_launches.load(); }
 int srfe_release_host_workspace(void) { return release_host_ws(); }
+
+int srfe_augment_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const int8_t* kind,
+                     int64_t first_clip_index, const int16_t* noise_bank, const int64_t* noise_offsets, int32_t n_noise_files,
+                     const srfe_augment_params* p, float* out, int8_t* op_out, void* stream) {
+    if (!p) return fail(SRFE_ERR_BAD_ARG, "params is NULL");
+    if (n_clips < 0 || n_samples <= 0 || clip_stride < n_samples) return fail(SRFE_ERR_BAD_ARG, "augment: bad sizes");
+    if (n_clips > 0 && (!pcm || !out)) return fail(SRFE_ERR_BAD_ARG, "pcm/out is NULL");
+    if (n_noise_files < 0 || (n_noise_files > 0 && (!noise_bank || !noise_offsets))) return fail(SRFE_ERR_BAD_ARG, "augment: noise bank is NULL");
+    if (n_clips > 0x7fffffffLL || n_samples > (1 << 24) || first_clip_index < 0) return fail(SRFE_ERR_TOO_LARGE, "n_clips / n_samples too large");
+    const bool needs_noise = kind != nullptr || p->noise_hi > p->noise_lo || p->snr_hi > p->snr_lo;
+    if (needs_noise && n_noise_files == 0) return fail(SRFE_ERR_BAD_ARG, "augment: the noise / silence ops need a background-noise bank");
+    if (p->shift_range < 0 || p->shift_range > n_samples) return fail(SRFE_ERR_BAD_ARG, "augment: shift_range out of [0, n_samples]");
+    if (n_clips == 0) return SRFE_OK;
+    AugParams a{};
+    a.pcm = pcm; a.out = out; a.kind = (const signed char*)kind; a.op_out = (signed char*)op_out;
+    a.bank = noise_bank; a.bank_off = (const long long*)noise_offsets;
+    a.clip_stride = clip_stride; a.first_index = first_clip_index;
+    a.n_clips = (int)n_clips; a.n_samples = (int)n_samples; a.n_files = n_noise_files;
+    a.key0 = (unsigned)(p->seed & 0xffffffffu); a.key1 = (unsigned)(p->seed >> 32);
+    a.shift_lo = p->shift_lo; a.shift_hi = p->shift_hi; a.noise_lo = p->noise_lo; a.noise_hi = p->noise_hi;
+    a.snr_lo = p->snr_lo; a.snr_hi = p->snr_hi; a.pitch_lo = p->pitch_lo; a.pitch_hi = p->pitch_hi;
+    a.speed_lo = p->speed_lo; a.speed_hi = p->speed_hi;
+    a.shift_range = p->shift_range; a.noise_upper = p->noise_upper;
+    const double snr_db[4] = {-5.0, 0.0, 5.0, 10.0};
+    for (int i = 0; i < 4; ++i) a.snr_div[i] = std::pow(10.0, snr_db[i] / 10.0);
+    srfe_augment_kernel<<<(unsigned)n_clips, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_augment_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SRFE_OK;
+}
 int srfe_set_tuning(const char* name, int value) {
     if (!name || value < 0) return fail(SRFE_ERR_BAD_ARG, "srfe_set_tuning: name is NULL or value < 0");
     for (int k = 0; k < TUNE_COUNT; ++k)

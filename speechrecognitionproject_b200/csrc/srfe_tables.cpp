@@ -48,6 +48,7 @@ int validate(const srfe_fbank_params& p, const char** why) {
     if (p.frame_step < 2 || p.frame_step % 2) { *why = "fbank: frame_step must be even and >= 2"; return SRFE_ERR_UNSUPPORTED; }
     if (p.nfilt < 1 || p.nfilt > 256) { *why = "fbank: need 1 <= nfilt <= 256"; return SRFE_ERR_UNSUPPORTED; }
     if (p.sample_rate <= 0) { *why = "fbank: sample_rate must be positive"; return SRFE_ERR_BAD_ARG; }
+    if (p.vtlp_alpha != 0.f && !(p.vtlp_alpha >= 0.5f && p.vtlp_alpha <= 2.f)) { *why = "fbank: vtlp_alpha must be 0 (off) or in [0.5, 2]"; return SRFE_ERR_BAD_ARG; }
     return SRFE_OK;
 }
 int validate(const srfe_mfcc_params& p, const char** why) {
@@ -100,7 +101,11 @@ void fbank_filters(const srfe_fbank_params& p, std::vector<double>& w) {
     linspace(0.0, high, p.nfilt + 2, mel);
     std::vector<double> bin(p.nfilt + 2);
     for (int i = 0; i < p.nfilt + 2; ++i) {
-        const double hz = 700.0 * (std::pow(10.0, mel[i] / 2595.0) - 1.0);
+        double hz = 700.0 * (std::pow(10.0, mel[i] / 2595.0) - 1.0);
+        if (p.vtlp_alpha != 0.f) {                           // legacy/model_8/dataset_top.py:251-252
+            const double a = (double)p.vtlp_alpha, nyq = p.sample_rate / 2.0, m1 = std::min(a, 1.0);
+            hz = hz < (4800.0 * m1 / a) ? hz * a : nyq - ((nyq - 4800.0 * m1) / (nyq - 4800.0 * (m1 / a))) * (nyq - hz);
+        }
         bin[i] = std::floor((p.n_fft + 1) * hz / p.sample_rate);
     }
     w.assign((size_t)p.nfilt * nb, 0.0);

@@ -69,12 +69,13 @@ class FbankParams:
     nfft: int = 512
     preemph: float = 0.97
     nfilt: int = 120
+    vtlp_alpha: float = 0.0     # 0 = off; legacy/model_8/dataset_top.py:251-252 warps the filter centres by alpha ~ U(0.9, 1.1)
 
     def op_args(self) -> tuple:
-        return (self.fs, self.frame_len, self.frame_step, self.nfft, float(self.preemph), self.nfilt)
+        return (self.fs, self.frame_len, self.frame_step, self.nfft, float(self.preemph), self.nfilt, float(self.vtlp_alpha))
 
     def to_c(self) -> FbankParamsC:
-        return FbankParamsC(self.fs, self.frame_len, self.frame_step, self.nfft, self.preemph, self.nfilt)
+        return FbankParamsC(self.fs, self.frame_len, self.frame_step, self.nfft, self.preemph, self.nfilt, self.vtlp_alpha)
 
 
 @dataclass(frozen=True)
@@ -235,8 +236,8 @@ def _(pcm, fs, nperseg, noverlap, take_log, eps, layout):
 
 @torch.library.custom_op("srfe::fbank", mutates_args=(), device_types="cuda")
 def _fbank_op(pcm: torch.Tensor, fs: int, frame_len: int, frame_step: int, nfft: int, preemph: float,
-              nfilt: int) -> torch.Tensor:
-    cp = FbankParamsC(fs, frame_len, frame_step, nfft, preemph, nfilt)
+              nfilt: int, vtlp_alpha: float) -> torch.Tensor:
+    cp = FbankParamsC(fs, frame_len, frame_step, nfft, preemph, nfilt, vtlp_alpha)
     shp = (C.c_int64 * 2)()
     _lib.check(_lib.lib().srfe_fbank_out_shape(C.byref(cp), pcm.size(1), C.byref(shp)))
     out = torch.empty((pcm.size(0), shp[0], shp[1]), dtype=torch.float32, device=pcm.device)
@@ -245,7 +246,7 @@ def _fbank_op(pcm: torch.Tensor, fs: int, frame_len: int, frame_step: int, nfft:
 
 
 @_fbank_op.register_fake
-def _(pcm, fs, frame_len, frame_step, nfft, preemph, nfilt):
+def _(pcm, fs, frame_len, frame_step, nfft, preemph, nfilt, vtlp_alpha):
     t = -(-abs(pcm.size(1) - frame_len) // frame_step)
     return pcm.new_empty((pcm.size(0), t, nfilt), dtype=torch.float32)
 

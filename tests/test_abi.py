@@ -117,6 +117,19 @@ def test_filterbanks_match_oracle(srfe_lib):
         p = S.PRESETS[name]
         fb = _tab(srfe_lib.srfe_fbank_filters_f64, p.to_c(), p.nfilt * 257).reshape(p.nfilt, 257)
         np.testing.assert_array_equal(fb, oracle.htk_floor_filterbank(oracle.PRESETS[name]))   # floor() bins: exact
+    # VTLP-warped banks (legacy/model_8/dataset_top.py:251-252), alpha over the reference's U(0.9, 1.1) range and its ends
+    from dataclasses import replace
+    base = oracle.htk_floor_filterbank(oracle.R_FBANK)
+    moved = 0
+    for alpha in (0.9, 0.93, 0.987, 1.0, 1.013, 1.07, 1.1):
+        for name in ("R-FBANK", "C-FBANK"):
+            p = replace(S.PRESETS[name], vtlp_alpha=alpha)
+            fb = _tab(srfe_lib.srfe_fbank_filters_f64, p.to_c(), p.nfilt * 257).reshape(p.nfilt, 257)
+            want = oracle.htk_floor_filterbank(replace(oracle.PRESETS[name], vtlp_alpha=alpha))
+            np.testing.assert_array_equal(fb, want)
+            assert not fb[:, 256].any() or alpha > 1.0
+            moved += name == "R-FBANK" and not np.array_equal(fb, base)
+    assert moved >= 5                                                    # the warp does move the triangles
     for name in ("R-MFCC", "C-MFCC"):
         p = S.PRESETS[name]
         nb = p.n_fft // 2 + 1

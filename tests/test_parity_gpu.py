@@ -576,3 +576,16 @@ def test_mfcc_tensor_core_kernel_limits(srfe_lib):
         assert torch.equal(S.mfcc(x, p), y)
     finally:
         S.set_tuning()
+
+
+@pytest.mark.parametrize("alpha", [0.9, 1.0, 1.08])
+def test_fbank_vtlp_warped_bank(srfe_lib, corpus, alpha):
+    """the VTLP warp of legacy/model_8/dataset_top.py:251-252 as a filter-bank option (one alpha per call)."""
+    p = replace(S.R_FBANK, vtlp_alpha=alpha)
+    got = _gpu(S.fbank, corpus[:8], p)
+    truth = H.oracle_batch(oracle.fbank_truth, corpus[:8], H.to_oracle_params(p))
+    H.check_logmel(got, truth, f"vtlp {alpha}")
+    if alpha != 1.0:
+        assert np.abs(got - _gpu(S.fbank, corpus[:8], S.R_FBANK)).max() > 0.5       # and it is a different bank
+    with pytest.raises(RuntimeError, match="SRFE_ERR_BAD_ARG"):
+        S.fbank(torch.from_numpy(corpus[:2]).cuda(), replace(S.R_FBANK, vtlp_alpha=3.0))
