@@ -152,6 +152,19 @@ int srfe_fbank_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64
 int srfe_mfcc_i16 (const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                    const srfe_mfcc_params* p, float* out, void* cuda_stream);
 
+/* ---- several feature sets of the same batch in ONE launch ---- */
+/* The reference's ensemble pushes one batch through model_spec_* and model_fbanks_cnn in turn
+ * (analyst_training.py:91-94, predictions.py:58-60), each recomputing its features from the PCM.  These entry points
+ * produce the spectrogram AND the log-fbank features of the same clips with one kernel: a CTA takes a group of clips
+ * through both frame loops back to back, so HBM delivers every sample once for both outputs.  Results are bit-identical
+ * to srfe_spec_* and srfe_fbank_* called separately.  The fbank side needs n_fft = 512 (else SRFE_ERR_UNSUPPORTED). */
+int srfe_spec_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_spec_params* ps, const srfe_fbank_params* pf, float* out_spec, float* out_fbank,
+                        void* cuda_stream);
+int srfe_spec_fbank_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                        const srfe_spec_params* ps, const srfe_fbank_params* pf, float* out_spec, float* out_fbank,
+                        void* cuda_stream);
+
 /* ---- host entry points (pcm/out are HOST pointers; synchronous) ----------- */
 /* H2D of the batch, the same kernels, D2H of the features, on `device`, chunked over two streams so that the
  * transfers of one chunk overlap the kernel of the other.  Pinned (page-locked) caller buffers are copied from / to

@@ -9,7 +9,7 @@ functions and batched ops over the C ABI of ``include/srfe.h``) and
 from .features import (  # noqa: F401
     SpecParams, FbankParams, MfccParams, PRESETS,
     R_SPEC, C_SPEC, R_FBANK, C_FBANK, R_MFCC, C_MFCC, C_MFCC_D2,
-    spec, fbank, mfcc, compute_spec, filter_banks, compute_mfcc,
+    spec, fbank, mfcc, spec_fbank, compute_spec, filter_banks, compute_mfcc,
     out_shape, bytes_per_clip, launch_count, set_tuning, release_host_workspace,
 )
 from .patch import patch_model, SharedFrontEnd  # noqa: F401

@@ -613,6 +613,73 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
 #undef SRFE_GO
 }
 
+// ------------------------------------------------------------------------------
+// spectrogram + fbank of the same batch in one launch (srfe_spec_fbank_kernel)
+// ------------------------------------------------------------------------------
+template <int NA, int NB, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
+static int launch_fused_k(const KParams& ka, const KParams& kb, int off_b, int dev, int grid, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_spec_fbank_kernel<NA, NB, JLO, JHI, NG, CODE, SAMP>;
+    static std::atomic<int> attr_set[kMaxDevices];
+    if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
+        SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int cur = attr_set[dev].load(std::memory_order_relaxed);
+        while (cur < smem_bytes && !attr_set[dev].compare_exchange_weak(cur, smem_bytes, std::memory_order_release)) {}
+    }
+    kern<<<grid, kMaxThreads, smem_bytes, st>>>(ka, kb, off_b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_spec_fbank_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SRFE_OK;
+}
+
+static int run_fused(const void* pcm, bool i16, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                     const srfe_spec_params* ps, const srfe_fbank_params* pf, float* out_spec, float* out_fbank,
+                     cudaStream_t st, int64_t Ta, int64_t Tb) {
+    Entry *ea = nullptr, *eb = nullptr;
+    int rc = get_entry(FAM_SPEC, *ps, &ea);
+    if (rc == SRFE_OK) rc = get_entry(FAM_FBANK, *pf, &eb);
+    if (rc != SRFE_OK) return rc;
+    if (eb->n_fft != 512) return fail(SRFE_ERR_UNSUPPORTED, "spec+fbank in one launch: the fbank side needs n_fft = 512");
+    if (n_clips == 0 || Ta == 0 || Tb == 0) return SRFE_OK;
+    DevInfo* di = nullptr;
+    rc = dev_info(&di);
+    if (rc != SRFE_OK) return rc;
+    auto up = [](int x, int a) { return (x + a - 1) / a * a; };
+    const int warps = kMaxThreads / 32, hw = 2 * warps;
+    auto fill = [&](const Entry* e, KParams& k, float* out, int64_t T) {
+        k = e->kp;
+        k.pcm = pcm; k.out = out; k.clip_stride = clip_stride; k.n_clips = (int)n_clips; k.n_samples = (int)n_samples; k.T = (int)T;
+        k.blob_bytes = align16(e->blob_smem);
+        int scratch = hw * (e->n_fft == 512 ? FftGeom<512>::SCRATCH_P2 : FftGeom<640>::SCRATCH_P2) * 8;
+        if (e->family == FAM_SPEC && k.layout == SRFE_LAYOUT_FT) scratch = std::max(scratch, align16(e->n_bins * (2 * hw + 2) * 4));
+        k.sm_scratch = up(k.blob_bytes, 128);
+        k.sm_tile = k.sm_scratch + scratch;
+        k.t_magic = (unsigned)((0x100000000ULL + (unsigned long long)T - 1) / (unsigned long long)T);
+        return up(k.sm_tile, 128);
+    };
+    KParams ka, kb;
+    const int off_b = fill(ea, ka, out_spec, Ta);
+    const int smem = off_b + fill(eb, kb, out_fbank, Tb);
+    if (smem > di->smem_optin) return fail(SRFE_ERR_TOO_LARGE, "spec+fbank in one launch: shared memory plan does not fit");
+    int cpc = 8;                                                       // small batches: never trade CTAs for clips per group
+    while (cpc > 1 && ((n_clips + cpc - 1) / cpc < 2 * di->sms || 8.0 * cpc * std::max(Ta, Tb) >= 4294967296.0 / std::max(Ta, Tb))) cpc /= 2;
+    ka.cpc = kb.cpc = cpc;
+    ka.n_groups = kb.n_groups = (int)((n_clips + cpc - 1) / cpc);
+    const int grid = std::min(ka.n_groups, di->sms);
+    const int jlo = kb.w_lo / 32, jhi = (kb.w_hi + 31) / 32;
+    const bool a400 = eb->mel_ng == 8 && eb->mel_code == 0xa400u;
+#define SRFE_GO_F(NA, JLO, JHI, NG, CODE)                                                                                   \
+    return i16 ? launch_fused_k<NA, 512, JLO, JHI, NG, CODE, short>(ka, kb, off_b, di->index, grid, smem, st)               \
+               : launch_fused_k<NA, 512, JLO, JHI, NG, CODE, float>(ka, kb, off_b, di->index, grid, smem, st)
+    if (ea->n_fft == 640) {
+        if (jlo == 0 && jhi <= 13) { if (a400) SRFE_GO_F(640, 0, 13, 8, 0xa400u); SRFE_GO_F(640, 0, 13, 0, 0u); }
+        SRFE_GO_F(640, 0, 16, 0, 0u);
+    }
+    if (jlo == 0 && jhi <= 13) { if (a400) SRFE_GO_F(512, 0, 13, 8, 0xa400u); SRFE_GO_F(512, 0, 13, 0, 0u); }
+    SRFE_GO_F(512, 0, 16, 0, 0u);
+#undef SRFE_GO_F
+}
+
 static int check_buffers(const void* pcm, int elem, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const void* p,
                          const float* out) {
     if (!p) return fail(SRFE_ERR_BAD_ARG, "params is NULL");
@@ -826,6 +893,26 @@ int srfe_device_count(void) {
 }
 int64_t srfe_launch_count(void) { return g_launches.load(); }
 int srfe_release_host_workspace(void) { return release_host_ws(); }
+
+static int spec_fbank(const void* pcm, bool i16, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* ps,
+                      const srfe_fbank_params* pf, float* out_spec, float* out_fbank, void* stream) {
+    int rc = check_buffers(pcm, i16 ? 2 : 4, n_clips, n_samples, clip_stride, ps, out_spec);
+    if (rc == SRFE_OK) rc = check_buffers(pcm, i16 ? 2 : 4, n_clips, n_samples, clip_stride, pf, out_fbank);
+    if (rc != SRFE_OK) return rc;
+    const int64_t Ta = srfe_spec_out_shape(ps, n_samples, nullptr);
+    if (Ta < 0) return (int)Ta;
+    const int64_t Tb = srfe_fbank_out_shape(pf, n_samples, nullptr);
+    if (Tb < 0) return (int)Tb;
+    return run_fused(pcm, i16, n_clips, n_samples, clip_stride, ps, pf, out_spec, out_fbank, (cudaStream_t)stream, Ta, Tb);
+}
+int srfe_spec_fbank_f32(const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* ps,
+                        const srfe_fbank_params* pf, float* out_spec, float* out_fbank, void* stream) {
+    return spec_fbank(pcm, false, n_clips, n_samples, clip_stride, ps, pf, out_spec, out_fbank, stream);
+}
+int srfe_spec_fbank_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* ps,
+                        const srfe_fbank_params* pf, float* out_spec, float* out_fbank, void* stream) {
+    return spec_fbank(pcm, true, n_clips, n_samples, clip_stride, ps, pf, out_spec, out_fbank, stream);
+}
 
 int srfe_augment_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const int8_t* kind,
                      int64_t first_clip_index, const int16_t* noise_bank, const int64_t* noise_offsets, int32_t n_noise_files,

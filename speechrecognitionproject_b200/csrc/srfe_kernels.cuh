@@ -415,17 +415,11 @@ __device__ __forceinline__ void dct_items(const KParams& p, const P2* tileP, con
 // --------------------------------------------------------------------------------
 // NG / CODE: compile-time shape of the mel ELL bank (NG 16-filter groups, 2 bits per group = float4 steps - 1)
 // for the known presets, so the projection unrolls into straight-line code; NG = 0 -> runtime metadata.
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
-__global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
-    const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
-    typedef FftGeom<NFFT> G;
-    constexpr int F = G::M + 1;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const int HW = nthr >> 4;
-
-    {   // tables -> shared memory, once per (persistent) CTA
+// tables -> shared memory, once per (persistent) CTA; the caller synchronises the CTA afterwards
+template <int FAM>
+__device__ __forceinline__ void srfe_load_tables(const KParams& p, unsigned char* smem) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    {
         const int4* src = reinterpret_cast<const int4*>(p.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < p.blob_bytes / 16; i += nthr) dst[i] = __ldg(src + i);
@@ -440,6 +434,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
         int4* z = reinterpret_cast<int4*>(smem + p.sm_scratch);
         for (int i = tid; i < (p.sm_tile - p.sm_scratch) / 16; i += nthr) z[i] = make_int4(0, 0, 0, 0);
     }
+}
+
+// the clip groups grp_begin, grp_begin + grp_step, ... < grp_end of one feature family; `smem` = this family's region
+// ([tables][scratch][tile], offsets in p).  srfe_kernel runs one family over the CTA's share of all groups; the fused
+// kernel (below) alternates two families group by group so that the second one finds the PCM in L1 / L2.
+// GRID = true: the CTA's grid-stride share of all groups (bounds read from blockIdx / gridDim / p, not held in registers)
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP, bool GRID>
+__device__ __forceinline__ void srfe_groups(const KParams& p, unsigned char* smem_region, int grp_begin, int grp_end, int grp_step) {
+    extern __shared__ __align__(128) unsigned char smem_base[];
+    unsigned char* smem = GRID ? smem_base : smem_region;   // single-family kernel: addresses fold to constants, no base register
+    const SAMP* pcm = reinterpret_cast<const SAMP*>(p.pcm);
+    typedef FftGeom<NFFT> G;
+    constexpr int F = G::M + 1;
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int HW = nthr >> 4;
+
     const float* s_win = reinterpret_cast<const float*>(smem + p.off_win);
     FftTables T;
     T.tw1 = reinterpret_cast<const cpx*>(smem + p.off_tw1);
@@ -455,12 +466,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     P2* tileP = reinterpret_cast<P2*>(tile);
     P2* fmeanP = tileP + (((p.T + 1) >> 1) + 1) * p.tile_stride;      // per-pair frame means, right after the tile
     const float* s_dfold = reinterpret_cast<const float*>(smem + p.off_dfold);
-    __syncthreads();
 
     const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
     P2* xb = scratch_all + hw * G::SCRATCH_P2;           // this half-warp's exchange tile / packed power buffer
 
-    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+    for (int grp = GRID ? (int)blockIdx.x : grp_begin; grp < (GRID ? p.n_groups : grp_end); grp += GRID ? (int)gridDim.x : grp_step) {
         const int clip0 = grp * p.cpc;
         const int ncl = min(p.cpc, p.n_clips - clip0);
         const int nf = ncl * p.T;                           // flattened frames of this group
@@ -752,6 +762,34 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
             }
             __syncthreads();                                // scratch / tile are reused by the next clip
         }
+    }
+}
+
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
+__global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    srfe_load_tables<FAM>(p, smem);
+    __syncthreads();
+    srfe_groups<NFFT, FAM, JLO, JHI, NG, CODE, SAMP, true>(p, smem, 0, 0, 0);
+}
+
+// --------------------------------------------------------------------------------
+// spectrogram + log-fbank of the SAME clips in one launch: the reference's ensemble feeds one batch to
+// model_spec_* and model_fbanks_cnn in turn (analyst_training.py:91-94, predictions.py:58-60), each recomputing its
+// features from the PCM.  Here a CTA takes a group of clips through the spectrogram frames and then, straight away,
+// through the fbank frames (different framing: 640 / 320 vs 400 / 160, so the FFTs are not shared): the second pass finds
+// the group's samples in L1 / L2, HBM delivers each sample once for both outputs.  Both families keep their own
+// [tables][scratch] region of shared memory; pa.cpc == pb.cpc and pa.n_groups == pb.n_groups (host).
+// --------------------------------------------------------------------------------
+template <int NA, int NB, int JLO_B, int JHI_B, int NG_B, unsigned CODE_B, typename SAMP>
+__global__ void __launch_bounds__(kMaxThreads, 1) srfe_spec_fbank_kernel(const KParams pa, const KParams pb, int off_b) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    srfe_load_tables<FAM_SPEC>(pa, smem);
+    srfe_load_tables<FAM_FBANK>(pb, smem + off_b);
+    __syncthreads();
+    for (int grp = blockIdx.x; grp < pa.n_groups; grp += gridDim.x) {
+        srfe_groups<NA, FAM_SPEC, 0, NA / 32, 0, 0u, SAMP, false>(pa, smem, grp, grp + 1, 1);
+        srfe_groups<NB, FAM_FBANK, JLO_B, JHI_B, NG_B, CODE_B, SAMP, false>(pb, smem + off_b, grp, grp + 1, 1);
     }
 }
 

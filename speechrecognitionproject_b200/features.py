@@ -31,7 +31,7 @@ from ._lib import LAYOUT_FT, LAYOUT_TF, FbankParamsC, MfccParamsC, SpecParamsC
 __all__ = [
     "SpecParams", "FbankParams", "MfccParams", "PRESETS",
     "R_SPEC", "C_SPEC", "R_FBANK", "C_FBANK", "R_MFCC", "C_MFCC", "C_MFCC_D2",
-    "spec", "fbank", "mfcc", "compute_spec", "filter_banks", "compute_mfcc",
+    "spec", "fbank", "mfcc", "spec_fbank", "compute_spec", "filter_banks", "compute_mfcc",
     "out_shape", "bytes_per_clip", "launch_count", "set_tuning", "release_host_workspace",
 ]
 
@@ -317,6 +317,29 @@ def mfcc(x: torch.Tensor, params: MfccParams = R_MFCC, *, layout: Optional[str] 
     if layout is not None and layout != params.layout:
         params = replace(params, layout=layout)
     return _dispatch("mfcc", params, x, device)
+
+
+def spec_fbank(x: torch.Tensor, spec_params: SpecParams = R_SPEC, fbank_params: FbankParams = R_FBANK, *,
+               layout: Optional[str] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Spectrogram AND log-fbank features of the same CUDA batch in ONE launch (``srfe_spec_fbank_*``): what
+    the reference's ensemble computes twice from the same ``batch['audio']`` (analyst_training.py:91-94).  Bit-identical
+    to ``spec(x, ...)`` and ``fbank(x, ...)``; the PCM is read from HBM once for both."""
+    if layout is not None and layout != spec_params.layout:
+        spec_params = replace(spec_params, layout=layout)
+    if not x.is_cuda:
+        raise TypeError("spec_fbank: expected a CUDA tensor (host batches: upload once, then call this)")
+    single = x.dim() == 1
+    xb = _prep(x.unsqueeze(0) if single else x)
+    n = xb.size(0)
+    ys = torch.empty((n,) + _cached_shape(spec_params, xb.size(1)), dtype=torch.float32, device=xb.device)
+    yf = torch.empty((n,) + _cached_shape(fbank_params, xb.size(1)), dtype=torch.float32, device=xb.device)
+    fn = getattr(_lib.lib(), f"srfe_spec_fbank_{_suffix(xb)}")
+    stride = xb.stride(0) if n > 1 else xb.size(1)
+    with torch.cuda.device(xb.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(fn(xb.data_ptr(), n, xb.size(1), stride, C.byref(_c_params(spec_params)), C.byref(_c_params(fbank_params)),
+                      ys.data_ptr(), yf.data_ptr(), stream))
+    return (ys[0], yf[0]) if single else (ys, yf)
 
 
 # ------------------------------------------------------------------------------------

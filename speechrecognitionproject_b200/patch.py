@@ -65,8 +65,12 @@ class SharedFrontEnd:
         self._dev = None
         self._pcm = None
         self._feat = {}
+        self._members = set()       # feature sets the ensemble's members consume (filled by patch_model)
         self.uploads = 0            # statistics (tests, logs)
         self.launches = 0
+
+    def register(self, name: str) -> None:
+        self._members.add(name)
 
     def pcm(self, x: torch.Tensor, dev: torch.device) -> torch.Tensor:
         if x is not self._src or x._version != self._version or dev != self._dev:
@@ -82,25 +86,41 @@ class SharedFrontEnd:
     def features(self, name: str, fn: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, dev: torch.device):
         xd = self.pcm(x, dev)
         if name not in self._feat:
-            self._feat[name] = fn(xd)
+            if name in ("spec_tf", "fbank_tf") and {"spec_tf", "fbank_tf"} <= self._members and xd.is_cuda and fn is _DEFAULT_FN.get(name):
+                # a spectrogram member and the fbank member share the batch: both feature sets from ONE launch, the PCM
+                # read from HBM once (features.spec_fbank; bit-identical to the separate calls)
+                self._feat["spec_tf"], self._feat["fbank_tf"] = F.spec_fbank(xd, F.R_SPEC, F.R_FBANK, layout="tf")
+            else:
+                self._feat[name] = fn(xd)
             self.launches += 1
         return self._feat[name]
 
     def clear(self) -> None:
+        members = self._members
         self.__init__()
+        self._members = members
+
+
+def _mfcc_tf(x):
+    return F.mfcc(x, F.R_MFCC, layout="tf")            # [B,51,39] == transpose(inx,1,2)
+
+
+def _spec_tf(x):
+    return F.spec(x, F.R_SPEC, layout="tf")            # [B,49,321] == transpose(inx,1,2) (bgru) == compute_spec(...).T (cnn)
+
+
+def _fbank_tf(x):
+    return F.fbank(x, F.R_FBANK)                       # [B,98,120]
+
+
+_DEFAULT_FN = {"mfcc_tf": _mfcc_tf, "spec_tf": _spec_tf, "fbank_tf": _fbank_tf}
 
 
 def default_feature_fn(kind: str) -> Callable[[torch.Tensor], torch.Tensor]:
     """Batched device features in the layout the model's first layer consumes."""
-    if kind in ("mfcc_bgru", "mfrn_bgru"):
-        return lambda x: F.mfcc(x, F.R_MFCC, layout="tf")          # [B,51,39] == transpose(inx,1,2)
-    if kind == "spec_bgru":
-        return lambda x: F.spec(x, F.R_SPEC, layout="tf")          # [B,49,321] == transpose(inx,1,2)
-    if kind == "spec_cnn":
-        return lambda x: F.spec(x, F.R_SPEC, layout="tf")          # [B,49,321] (compute_spec(...).T)
-    if kind == "fbanks_cnn":
-        return lambda x: F.fbank(x, F.R_FBANK)                     # [B,98,120]
-    raise ValueError(kind)
+    if kind not in _FEATURE_SET:
+        raise ValueError(kind)
+    return _DEFAULT_FN[_FEATURE_SET[kind]]
 
 
 def _cnn_tail(self, x):
@@ -130,6 +150,8 @@ def make_forward(kind: str, feature_fn: Optional[Callable] = None, frontend: Opt
     if kind not in _KINDS:
         raise ValueError(f"unknown model kind {kind!r}; expected one of {_KINDS}")
     feat = feature_fn or default_feature_fn(kind)
+    if frontend is not None:
+        frontend.register(_FEATURE_SET[kind])
 
     def forward(self, x):
         dev = next(self.parameters()).device

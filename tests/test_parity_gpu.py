@@ -589,3 +589,25 @@ def test_fbank_vtlp_warped_bank(srfe_lib, corpus, alpha):
         assert np.abs(got - _gpu(S.fbank, corpus[:8], S.R_FBANK)).max() > 0.5       # and it is a different bank
     with pytest.raises(RuntimeError, match="SRFE_ERR_BAD_ARG"):
         S.fbank(torch.from_numpy(corpus[:2]).cuda(), replace(S.R_FBANK, vtlp_alpha=3.0))
+
+
+@pytest.mark.parametrize("names", [("R-SPEC", "R-FBANK"), ("C-SPEC", "C-FBANK"), ("C-SPEC", "R-FBANK"), ("R-SPEC", "C-FBANK")])
+def test_spec_and_fbank_in_one_launch(srfe_lib, corpus, names):
+    """srfe_spec_fbank_* = the two feature sets the reference's ensemble computes from the same batch
+    (analyst_training.py:91-94) out of one kernel; bit-identical to the separate entry points."""
+    ps, pf = S.PRESETS[names[0]], S.PRESETS[names[1]]
+    x = torch.from_numpy(np.concatenate([corpus] * 14)[:331]).cuda()
+    for n in (1, 5, 331):
+        for layout in ("ft", "tf"):
+            n0 = S.launch_count()
+            ys, yf = S.spec_fbank(x[:n], ps, pf, layout=layout)
+            assert S.launch_count() - n0 == 1
+            assert torch.equal(ys, S.spec(x[:n], ps, layout=layout)) and torch.equal(yf, S.fbank(x[:n], pf))
+    ys16, yf16 = S.spec_fbank(x.to(torch.int16), ps, pf)
+    assert torch.equal(ys16, S.spec(x, ps)) and torch.equal(yf16, S.fbank(x, pf))
+    y1s, y1f = S.spec_fbank(x[3], ps, pf)                                   # single clip
+    assert torch.equal(y1s, S.spec(x[3], ps)) and torch.equal(y1f, S.fbank(x[3], pf))
+    with pytest.raises(RuntimeError, match="SRFE_ERR_UNSUPPORTED"):
+        S.spec_fbank(x[:4], ps, replace(pf, nfft=640, frame_len=640))
+    with pytest.raises(TypeError):
+        S.spec_fbank(x[:4].cpu(), ps, pf)

@@ -257,13 +257,17 @@ def test_shared_front_end_gpu(srfe_lib):
     x = torch.from_numpy(oracle.synthetic_corpus(3, config_index=10))
     with torch.no_grad():
         want = {k: n(x) for k, n in nets.items()}          # reference-style CPU loops with oracle features
+    import speechrecognitionproject_b200 as S
     fe = patch.SharedFrontEnd()
     for k, m in mods.items():
         nets[k].cuda()
         patch.patch_model(m, kind=k, frontend=fe)
+    n0 = S.launch_count()
     with torch.no_grad():
         got = {k: n(x) for k, n in nets.items()}
-    assert fe.uploads == 1 and fe.launches == 3             # one PCM H2D; spec, fbank, mfcc once each
+    # one PCM H2D; the spectrogram (shared by both spec models) and the fbank features come out of ONE fused launch
+    # (srfe_spec_fbank_kernel), MFCC out of a second one
+    assert fe.uploads == 1 and fe.launches == 2 and S.launch_count() - n0 == 2
     for k in mods:
         # bins / bands far below the clip maximum differ between any two fp32 FFTs (tests/tolerances.py is level-aware
         # for that reason); through a few hundred random input weights that is worth a few 1e-3 on a logit.  Feature
