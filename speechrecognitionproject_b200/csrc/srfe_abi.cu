@@ -663,6 +663,7 @@ static int run_fused(const void* pcm, bool i16, int64_t n_clips, int64_t n_sampl
     if (smem > di->smem_optin) return fail(SRFE_ERR_TOO_LARGE, "spec+fbank in one launch: shared memory plan does not fit");
     int cpc = 8;                                                       // small batches: never trade CTAs for clips per group
     while (cpc > 1 && ((n_clips + cpc - 1) / cpc < 2 * di->sms || 8.0 * cpc * std::max(Ta, Tb) >= 4294967296.0 / std::max(Ta, Tb))) cpc /= 2;
+    if (tune(TUNE_CPC) > 0) cpc = tune(TUNE_CPC);
     ka.cpc = kb.cpc = cpc;
     ka.n_groups = kb.n_groups = (int)((n_clips + cpc - 1) / cpc);
     const int grid = std::min(ka.n_groups, di->sms);

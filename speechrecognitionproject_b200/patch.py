@@ -66,6 +66,7 @@ class SharedFrontEnd:
         self._pcm = None
         self._feat = {}
         self._members = set()       # feature sets the ensemble's members consume (filled by patch_model)
+        self.fuse_max_clips = 256   # spec + fbank from one launch up to this batch size (see features())
         self.uploads = 0            # statistics (tests, logs)
         self.launches = 0
 
@@ -86,9 +87,13 @@ class SharedFrontEnd:
     def features(self, name: str, fn: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, dev: torch.device):
         xd = self.pcm(x, dev)
         if name not in self._feat:
-            if name in ("spec_tf", "fbank_tf") and {"spec_tf", "fbank_tf"} <= self._members and xd.is_cuda and fn is _DEFAULT_FN.get(name):
+            if (name in ("spec_tf", "fbank_tf") and {"spec_tf", "fbank_tf"} <= self._members and xd.is_cuda
+                    and fn is _DEFAULT_FN.get(name) and xd.size(0) <= self.fuse_max_clips):
                 # a spectrogram member and the fbank member share the batch: both feature sets from ONE launch, the PCM
-                # read from HBM once (features.spec_fbank; bit-identical to the separate calls)
+                # read from HBM once (features.spec_fbank; bit-identical to the separate calls).  Measured on B200: 33 us
+                # against 49 us for two launches up to 64 clips (the reference's ensemble drivers run batch_size = 1,
+                # analyst_training.py:84); from ~512 clips on two launches are as fast or faster (1.52 vs 1.80 ms at 16,384:
+                # both kernels are bound on chip, not by the PCM read), so large batches keep them.
                 self._feat["spec_tf"], self._feat["fbank_tf"] = F.spec_fbank(xd, F.R_SPEC, F.R_FBANK, layout="tf")
             else:
                 self._feat[name] = fn(xd)
@@ -96,9 +101,9 @@ class SharedFrontEnd:
         return self._feat[name]
 
     def clear(self) -> None:
-        members = self._members
+        members, fuse = self._members, self.fuse_max_clips
         self.__init__()
-        self._members = members
+        self._members, self.fuse_max_clips = members, fuse
 
 
 def _mfcc_tf(x):
