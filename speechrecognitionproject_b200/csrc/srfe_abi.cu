@@ -458,20 +458,25 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
             Config pl{};
             const int smem = smem_plan(e, kp, warps, budget, &pl);
             if (smem < 0 || smem > budget) continue;
-            for (int cpc = 1; cpc <= cpc_max; cpc *= 2) {
+            for (int cpc = 1; cpc <= cpc_max; ++cpc) {
                 // small batches: never trade CTAs for clips per group (8 clips as one group would run on one SM)
-                if (cpc > 1 && (kp.n_clips + cpc - 1) / cpc < 2 * di.sms) break;
+                const long long groups = ((long long)kp.n_clips + cpc - 1) / cpc, slots = (long long)di.sms * ctas;
+                if (cpc > 1 && groups < slots) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
                 // Fitted to scripts/tune.py sweeps on the B200 (profiles/r1_notes.md): throughput ~ round efficiency x
                 // (resident warps - 2.3)^0.8.  Kernels with CTA barriers (MFCC epilogue, FT spectrogram tile) gain from a
                 // second co-resident CTA whose frame phase fills the first one's serial phase (MFCC ~1.6x at equal warps,
                 // and partly filled rounds then cost half as much); barrier-free kernels (TF spectrogram, FBANK) prefer
-                // one wide CTA and many clips per group (fewer group prologues).
+                // one wide CTA and many clips per group (fewer group prologues).  Round 2: any clips-per-group count (not
+                // only powers of two) and the persistent grid's own quantisation -- the busiest CTA runs
+                // ceil(groups / slots) groups -- so that BASELINE's small batches (cfg2: 1,024 clips = 6.9 clips per SM)
+                // are cut into groups that fill whole rounds AND whole waves.
                 const bool ft = e->family == FAM_SPEC && kp.layout == SRFE_LAYOUT_FT;
                 const bool mf = e->family == FAM_MFCC;
                 double eff = (double)nf / (double)(rounds * per_round);
                 if (mf && ctas == 2) eff = std::sqrt(eff);
+                if (groups >= slots) eff *= (double)groups / (double)(((groups + slots - 1) / slots) * slots);
                 double score = eff * std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
                 if (ctas == 2) score *= mf ? 1.6 : ft ? 1.1 : 0.92;
                 score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 + 0.01 * std::log2((double)cpc);
@@ -543,7 +548,7 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
         // remember it -- small-batch callers (the reference's ensemble drivers run batch_size = 1) pay for the search once
         bool overridden = false;
         for (int k = TUNE_WARPS; k <= TUNE_DCT_PQ; ++k) overridden = overridden || tune(k) > 0;
-        const ConfigKey key{e, kp.T, std::min(kp.n_clips, 16 * di->sms), kp.layout, di};   // beyond that every cpc is allowed
+        const ConfigKey key{e, kp.T, std::min(kp.n_clips, 64 * di->sms), kp.layout, di};   // beyond that the grid's quantisation is < 2 %
         bool hit = false;
         if (!overridden) {
             std::shared_lock<std::shared_mutex> lk(g_mu);
