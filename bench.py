@@ -413,8 +413,8 @@ def run_native(args) -> None:
             "config": make_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_clip": bpc,
-                         "kernel_ms_avg": avg_kern_ms, "kernel": "srfe_kernel<512, MFCC>",
-                         "note": "FP32-pipe bound, not HBM bound: see DESIGN.md"},
+                         "kernel_ms_avg": avg_kern_ms, "kernel": "srfe_mfcc_tc_kernel<512, ...> (tcgen05 DCT, TMEM accumulators)",
+                         "note": "bound by the shared-memory pipe (74 % of peak, ncu) and FP32 issue, not by HBM: DESIGN.md section 5"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(e2e_clips * N_SAMPLES * 4),
                     "d2h_bytes_per_step": d2h},
             "e2e_int16_ingest": {"value": e2e16_value, "unit": "clips/s", "h2d_bytes_per_step": int(e2e_clips * N_SAMPLES * 2),

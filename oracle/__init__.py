@@ -18,10 +18,13 @@ Pinning status: the reference ships no tests, fixtures or golden vectors, so
 "parity" is pinned on outputs of the reference functions themselves, run in the
 build container by ``oracle/make_golden.py`` (spec and fbank import and run
 unmodified from /root/reference; MFCC cannot, because librosa is absent, and is
-cross-checked against two independent implementations instead:
-``transformers.audio_utils`` and ``torchaudio``).  MFCC parity is therefore
-"pinned to the restatement + cross-checks", NOT to a librosa run: **MFCC parity
-unpinned by the reference itself.**
+cross-checked LIVE -- tests/test_mfcc_crosscheck.py, both parameter sets -- against
+two independent implementations instead: ``transformers.audio_utils`` and
+``torchaudio``, oracle/crosscheck.py).  MFCC parity is therefore "pinned to the
+restatement + cross-checks", NOT to a librosa run: **MFCC parity unpinned by the
+reference itself.**  ``oracle/augment.py`` (augmentation, dataset.py:107-202) has no
+reference test either and replaces the reference's global RNG by a counter-based
+stream by design: **parity unpinned**, arithmetic restated line by line.
 """
 from .features import (  # noqa: F401
     SpecParams, FbankParams, MfccParams,

@@ -1,0 +1,28 @@
+#!/bin/bash
+# one 8-GPU box: cfg5 (model_mfcc_bgru end to end) at 1/2/4/8 GPUs, then the headline bench at 2/4/8 for the e2e / H2D-ceiling table
+set -x
+rm -f gpurun_out/r2_cfg5.jsonl gpurun_out/r2_scale.jsonl
+port=29500
+for n in 1 2 4 8; do
+  port=$((port+1))
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
+      scripts/cfg5_model_mfcc_bgru.py --out gpurun_out/r2_cfg5.jsonl > gpurun_out/r2_cfg5_$n.log 2>&1 || tail -5 gpurun_out/r2_cfg5_$n.log
+done
+for n in 1 2 4 8; do
+  port=$((port+1))
+  if [ $n -eq 1 ]; then
+    timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-presets --no-cpu-baseline >> gpurun_out/r2_scale.jsonl 2> gpurun_out/r2_scale_$n.err
+  else
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
+      bench.py --gpus $n --steps 10 --warmup 3 >> gpurun_out/r2_scale.jsonl 2> gpurun_out/r2_scale_$n.err
+  fi
+done
+cat gpurun_out/r2_cfg5.jsonl
+python - <<'PY'
+import json
+for l in open("gpurun_out/r2_scale.jsonl"):
+    l=l.strip()
+    if not l.startswith("{"): continue
+    d=json.loads(l)
+    print(d["n_gpus"], round(d["value"]/1e6,2), "e2e", round(d["e2e"]["value"]/1e6,3), "i16", round(d["e2e_int16_ingest"]["value"]/1e6,3), "pageable", round(d["e2e_pageable_host"]["value"]/1e6,3), "h2d GB/s", round(d["e2e_h2d_ceiling"]["GBps"],1), "frac", round(d["e2e_h2d_ceiling"]["e2e_frac"],3))
+PY
