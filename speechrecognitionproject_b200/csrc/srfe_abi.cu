@@ -383,12 +383,28 @@ static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_ou
     return *smem_out <= di.smem_optin;
 }
 
+template <int NFFT, typename SAMP>
+static int launch_staged(const KParams& kp, int dev, int grid, int threads, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_spec_staged_kernel<NFFT, SAMP>;
+    static std::atomic<int> attr_set[kMaxDevices];
+    if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
+        SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int cur = attr_set[dev].load(std::memory_order_relaxed);
+        while (cur < smem_bytes && !attr_set[dev].compare_exchange_weak(cur, smem_bytes, std::memory_order_release)) {}
+    }
+    kern<<<grid, threads, smem_bytes, st>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_spec_staged_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SRFE_OK;
+}
+
 struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_var, dct_pq; };
 
 // Launch-shape overrides (srfe_set_tuning; 0 = automatic).  A test / tuning hook: results never depend on them
 // (tests/test_parity_gpu.py::test_results_do_not_depend_on_launch_configuration); no environment is read on the hot path.
-enum Tuning { TUNE_WARPS = 0, TUNE_CTAS, TUNE_CPC, TUNE_DCT_CB, TUNE_DCT_PQ, TUNE_MFCC_TC, TUNE_COUNT };
-static const char* const kTuningNames[TUNE_COUNT] = {"warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc"};
+enum Tuning { TUNE_WARPS = 0, TUNE_CTAS, TUNE_CPC, TUNE_DCT_CB, TUNE_DCT_PQ, TUNE_MFCC_TC, TUNE_STAGE, TUNE_COUNT };
+static const char* const kTuningNames[TUNE_COUNT] = {"warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc", "stage"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static int tune(int which) { return g_tune[which].load(std::memory_order_relaxed); }
 
@@ -583,6 +599,28 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
 #endif
     const int smem = cfg.smem;
     const int grid = std::min(kp.n_groups, di->sms * cfg.ctas), threads = 32 * cfg.warps;
+    if (e->family == FAM_SPEC && tune(TUNE_STAGE) == 2) {
+        // Spectrogram with TMA-staged frames (srfe_spec_staged_kernel): every half-warp prefetches its next frame pair into
+        // shared memory with cp.async.bulk + mbarrier while it transforms the current one.  Built, bit-identical, measured on
+        // B200 -- and NOT dispatched by default: C-SPEC TF 33.4 vs 35.4 M clips/s, C-SPEC FT 24.4 vs 24.5, R-SPEC TF (int16)
+        // 22.1 vs 25.6; the direct LDG.64 path already keeps enough loads in flight, and the staged copy costs an extra
+        // trip through the shared-memory pipe, which is the scarcer resource here (profiles/r2_notes.md).  Opt in with
+        // srfe_set_tuning("stage", 2).  Needs 16-byte aligned frame starts and room for one 2-frame buffer per half-warp.
+        if (cfg.ctas != 1) return fail(SRFE_ERR_UNSUPPORTED, "stage = 2: needs the one-CTA-per-SM plan");
+        const size_t elem = i16 ? 2 : 4;
+        const int stage = 2 * cfg.warps * 2 * e->n_fft * (int)elem, mb = 2 * cfg.warps * 8;
+        const bool aligned = ((uintptr_t)kp.pcm % 16 == 0) && ((size_t)kp.clip_stride * elem % 16 == 0) && ((size_t)kp.hop * elem % 16 == 0);
+        const int total = ((smem + 127) / 128) * 128 + stage + mb;
+        if (aligned && total <= di->smem_optin) {
+            kp.sm_stage = ((smem + 127) / 128) * 128;
+            kp.sm_stage_mb = kp.sm_stage + stage;
+            kp.stage_phase0 = 0;
+            if (e->n_fft == 512) return i16 ? launch_staged<512, short>(kp, di->index, grid, threads, total, st) : launch_staged<512, float>(kp, di->index, grid, threads, total, st);
+            return i16 ? launch_staged<640, short>(kp, di->index, grid, threads, total, st) : launch_staged<640, float>(kp, di->index, grid, threads, total, st);
+        } else if (tune(TUNE_STAGE) == 2) {
+            return fail(SRFE_ERR_UNSUPPORTED, "stage = 2: frames not 16-byte aligned or no shared memory left for the staging buffers");
+        }
+    }
     // Curated instantiation list.  Window extents (units of 32 samples) and the preset shapes of the mel
     // bank / DCT get specialised kernels; everything else runs the generic ones.
     //   mel {8 groups, 0xa400}: 128 Slaney mels @ n_fft 512 and the reference's 120 HTK bands @ 512

@@ -70,6 +70,8 @@ struct KParams {
     int sm_scratch, sm_tile;           // byte offsets into dynamic shared memory
     int tile_stride;                   // MFCC dB tile row stride (P2 units, odd)
     int w_lo, w_hi;                    // non-zero extent of the window (host: picks the JLO / JHI instantiation)
+    int sm_stage, sm_stage_mb;         // staged spectrogram: per-half-warp 2-frame buffers and mbarriers (shared-memory offsets)
+    unsigned stage_phase0;             //   (always 0: the barriers are initialised by the kernel)
     // tcgen05 MFCC kernel (srfe_mfcc_tc.cuh)
     int tc_b_src, tc_b_bytes, tc_off_b;        // DCT B operand (hi / lo, UMMA layout): offset in the global blob, bytes, shared-memory offset
     int tc_ne, tc_no, tc_tmem_cols;            // accumulator widths (even / odd coefficients, multiples of 16), TMEM columns to allocate
@@ -88,6 +90,14 @@ template <typename S> __device__ __forceinline__ float2 ld2(const S* q);
 template <> __device__ __forceinline__ float2 ld2<float>(const float* q) { return __ldg(reinterpret_cast<const float2*>(q)); }
 template <> __device__ __forceinline__ float2 ld2<short>(const short* q) {
     const short2 v = __ldg(reinterpret_cast<const short2*>(q));
+    return make_float2((float)v.x, (float)v.y);
+}
+
+// staged frames (shared memory, filled by cp.async.bulk): plain loads
+template <typename S> __device__ __forceinline__ float2 lds2(const S* q);
+template <> __device__ __forceinline__ float2 lds2<float>(const float* q) { return *reinterpret_cast<const float2*>(q); }
+template <> __device__ __forceinline__ float2 lds2<short>(const short* q) {
+    const short2 v = *reinterpret_cast<const short2*>(q);
     return make_float2((float)v.x, (float)v.y);
 }
 
@@ -113,9 +123,15 @@ struct RawFrame {
     bool final_;                       // samples already carry the pre-emphasis (edge path)
 };
 
-template <int FAM, int JLO, int JHI, typename S>
+template <int FAM, int JLO, int JHI, typename S, bool SMEM = false>
 __device__ __forceinline__ void fetch_frame(const KParams& p, const S* __restrict__ x, int base, int l,
                                             RawFrame<FAM, JHI - JLO>& r) {
+    if (SMEM) {                                             // x = the frame's staged copy, base = 0, always interior
+        r.final_ = false;
+#pragma unroll
+        for (int j = JLO; j < JHI; ++j) r.s[j - JLO] = lds2<S>(x + 2 * l + 32 * j);
+        return;
+    }
     const bool interior = (base + 32 * JLO >= 0) && (base + 32 * JHI <= p.n_samples);
     r.final_ = !interior;
     if (interior) {
@@ -243,9 +259,14 @@ __device__ __forceinline__ FramePos frame_pos(int f, int nf, int T, unsigned mag
 //   pa[r] / pb[r] = 4|X[k]|^2 / 4|X[M-k]|^2 of both frames for this lane's bins (k = l + 16 r for N = 512, bin640(l, r)
 //   for N = 640); returns 4|X[M/2]|^2 (meaningful on lane 0).  xb = the half-warp's exchange scratch.
 // --------------------------------------------------------------------------------
-template <int NFFT, int FAM, int JLO, int JHI, typename SAMP>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// SMEM: the two frames were staged in shared memory (clipA / clipB point at them, bases 0); `after_fetch` runs once the
+// samples sit in registers (the staging buffer may be refilled from there on)
+template <int NFFT, int FAM, int JLO, int JHI, typename SAMP, bool SMEM = false, typename Hook = NoHook>
 __device__ __forceinline__ P2 pair_power(const KParams& p, const SAMP* __restrict__ clipA, int baseA, const SAMP* __restrict__ clipB,
-                                         int baseB, int l, int lane, const float* s_win, const FftTables& T, P2* xb, P2* pa, P2* pb) {
+                                         int baseB, int l, int lane, const float* s_win, const FftTables& T, P2* xb, P2* pa, P2* pb,
+                                         Hook after_fetch = Hook()) {
     typedef FftGeom<NFFT> G;
     constexpr int NJ = JHI - JLO;
     // (holding the NEXT pair in registers was measured three ways -- fetched before the output stage, fetched
@@ -253,10 +274,11 @@ __device__ __forceinline__ P2 pair_power(const KParams& p, const SAMP* __restric
     //  registers / 12 warps: it spills or gains nothing; prefetch.global.L1 has no effect either.  The stall on
     //  the first use of the samples stays at ~6 % of warp time.)
     RawFrame<FAM, NJ> rawA, rawB;
-    fetch_frame<FAM, JLO, JHI, SAMP>(p, clipA, baseA, l, rawA);
-    fetch_frame<FAM, JLO, JHI, SAMP>(p, clipB, baseB, l, rawB);
+    fetch_frame<FAM, JLO, JHI, SAMP, SMEM>(p, clipA, baseA, l, rawA);
+    fetch_frame<FAM, JLO, JHI, SAMP, SMEM>(p, clipB, baseB, l, rawB);
     C2 v[G::V];
     window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
+    after_fetch();
     // The two planes of every exchange pass through the same slots: put / sync / get, twice.
     fft_pass1<NFFT>(v, l, T);
     C2 w[G::V];
@@ -440,7 +462,7 @@ __device__ __forceinline__ void srfe_load_tables(const KParams& p, unsigned char
 // ([tables][scratch][tile], offsets in p).  srfe_kernel runs one family over the CTA's share of all groups; the fused
 // kernel (below) alternates two families group by group so that the second one finds the PCM in L1 / L2.
 // GRID = true: the CTA's grid-stride share of all groups (bounds read from blockIdx / gridDim / p, not held in registers)
-template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP, bool GRID>
+template <int NFFT, int FAM, int JLO, int JHI, int NG, unsigned CODE, typename SAMP, bool GRID, bool STAGED = false>
 __device__ __forceinline__ void srfe_groups(const KParams& p, unsigned char* smem_region, int grp_begin, int grp_end, int grp_step) {
     extern __shared__ __align__(128) unsigned char smem_base[];
     unsigned char* smem = GRID ? smem_base : smem_region;   // single-family kernel: addresses fold to constants, no base register
@@ -469,6 +491,21 @@ __device__ __forceinline__ void srfe_groups(const KParams& p, unsigned char* sme
 
     const int hw = tid >> 4, l = tid & 15, lane = tid & 31;
     P2* xb = scratch_all + hw * G::SCRATCH_P2;           // this half-warp's exchange tile / packed power buffer
+    // STAGED (spectrogram): each half-warp owns a 2-frame staging buffer in shared memory and an mbarrier; one lane issues
+    // two cp.async.bulk (TMA, 1-D) copies for the half-warp's NEXT frame pair as soon as the current pair's samples are in
+    // registers, so the copy flies under the FFT and the next pair's samples come from shared memory, not from L1 / L2
+    SAMP* stg = reinterpret_cast<SAMP*>(smem + p.sm_stage) + hw * 2 * NFFT;
+    const unsigned stg_mb = (unsigned)__cvta_generic_to_shared(smem + p.sm_stage_mb + 8 * hw);
+    unsigned stg_phase = p.stage_phase0;                 // (the wrapper kernel initialises the barriers)
+    auto stage_issue = [&](const SAMP* fa, const SAMP* fb) {
+        constexpr unsigned kBytes = NFFT * sizeof(SAMP);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stg);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(stg_mb), "r"(2 * kBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(fa), "r"(kBytes), "r"(stg_mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst + kBytes), "l"(fb), "r"(kBytes), "r"(stg_mb) : "memory");
+    };
 
     for (int grp = GRID ? (int)blockIdx.x : grp_begin; grp < (GRID ? p.n_groups : grp_end); grp += GRID ? (int)gridDim.x : grp_step) {
         const int clip0 = grp * p.cpc;
@@ -478,15 +515,39 @@ __device__ __forceinline__ void srfe_groups(const KParams& p, unsigned char* sme
         const int rounds = (npairs + HW - 1) / HW;
         float run_max = -CUDART_INF_F;
 
+        bool staged_ahead = false;                          // STAGED: the copy for this iteration's pair is already in flight
         for (int it = 0; it < rounds; ++it) {
             const int q = it * HW + hw;
             P2 pa[G::M / 32], pb[G::M / 32], pmid;
             const bool active = (it * HW + (hw & ~1)) < npairs;
             if (active) {                                   // warp-uniform: both half-warps of a warp run together
                 const FramePos cA = frame_pos(2 * q, nf, p.T, p.t_magic, p.cpc), cB = frame_pos(2 * q + 1, nf, p.T, p.t_magic, p.cpc);
+                if (STAGED) {
+                    auto frame_ptr = [&](const FramePos& c) { return pcm + (long long)(clip0 + c.c) * p.clip_stride + p.start0 + c.t * p.hop; };
+                    if (!staged_ahead && l == 0) stage_issue(frame_ptr(cA), frame_ptr(cB));
+                    {   // the pair's samples have landed
+                        unsigned done = 0;
+                        while (!done)
+                            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                                         : "=r"(done) : "r"(stg_mb), "r"(stg_phase) : "memory");
+                        stg_phase ^= 1u;
+                    }
+                    const int qn = q + HW;                  // this half-warp's pair of the next round (same group)
+                    const bool more = (it + 1 < rounds) && ((it + 1) * HW + (hw & ~1)) < npairs;
+                    staged_ahead = more;
+                    auto refill = [&]() {
+                        __syncwarp();                       // every lane of the half-warp holds its samples in registers
+                        if (more && l == 0) {
+                            const FramePos nA = frame_pos(2 * qn, nf, p.T, p.t_magic, p.cpc), nB = frame_pos(2 * qn + 1, nf, p.T, p.t_magic, p.cpc);
+                            stage_issue(frame_ptr(nA), frame_ptr(nB));
+                        }
+                    };
+                    pmid = pair_power<NFFT, FAM, JLO, JHI, SAMP, true>(p, stg, 0, stg + NFFT, 0, l, lane, s_win, T, xb, pa, pb, refill);
+                } else {
                 pmid = pair_power<NFFT, FAM, JLO, JHI, SAMP>(p, pcm + (long long)(clip0 + cA.c) * p.clip_stride, p.start0 + cA.t * p.hop,
                                                               pcm + (long long)(clip0 + cB.c) * p.clip_stride, p.start0 + cB.t * p.hop,
                                                               l, lane, s_win, T, xb, pa, pb);
+                }
 
                 // bin held in slot r of this lane (and its mirror M - k): natural stride-16 order for N = 512,
                 // the radix-4 order of bin640() for N = 640
@@ -771,6 +832,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) srfe_kernel(const KParams p) {
     srfe_load_tables<FAM>(p, smem);
     __syncthreads();
     srfe_groups<NFFT, FAM, JLO, JHI, NG, CODE, SAMP, true>(p, smem, 0, 0, 0);
+}
+
+// spectrogram with TMA-staged frames (see srfe_groups: STAGED)
+template <int NFFT, typename SAMP>
+__global__ void __launch_bounds__(kMaxThreads, 1) srfe_spec_staged_kernel(const KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    srfe_load_tables<FAM_SPEC>(p, smem);
+    if (threadIdx.x < (blockDim.x >> 4)) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(smem + p.sm_stage_mb + 8 * threadIdx.x);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    srfe_groups<NFFT, FAM_SPEC, 0, NFFT / 32, 0, 0u, SAMP, true, true>(p, smem, 0, 0, 0);
 }
 
 // --------------------------------------------------------------------------------

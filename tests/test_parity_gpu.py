@@ -611,3 +611,22 @@ def test_spec_and_fbank_in_one_launch(srfe_lib, corpus, names):
         S.spec_fbank(x[:4], ps, replace(pf, nfft=640, frame_len=640))
     with pytest.raises(TypeError):
         S.spec_fbank(x[:4].cpu(), ps, pf)
+
+
+def test_spectrogram_with_tma_staged_frames(srfe_lib, corpus):
+    """srfe_spec_staged_kernel (cp.async.bulk + mbarrier prefetch of each half-warp's next frame pair; opt-in, see
+    srfe_abi.cu for why it is not the default): bit-identical to the direct-load kernel."""
+    x = torch.from_numpy(np.concatenate([corpus] * 14)[:333]).cuda()
+    try:
+        for p, xx in ((S.C_SPEC, x), (replace(S.C_SPEC, layout="tf"), x), (replace(S.R_SPEC, layout="tf"), x.to(torch.int16)),
+                      (replace(S.C_SPEC, log=False), x.to(torch.int16))):
+            for n in (1, 7, 148, 333):
+                S.set_tuning(stage=1, warps=16, ctas=1)
+                direct = S.spec(xx[:n], p)
+                S.set_tuning(stage=2, warps=16, ctas=1)
+                assert torch.equal(S.spec(xx[:n], p), direct), (p, n)
+        S.set_tuning(stage=2, warps=16, ctas=1)
+        with pytest.raises(RuntimeError, match="SRFE_ERR_UNSUPPORTED"):        # fp32 R-SPEC: 32 x 5 KB of staging do not fit
+            S.spec(x[:8], S.R_SPEC)
+    finally:
+        S.set_tuning()
