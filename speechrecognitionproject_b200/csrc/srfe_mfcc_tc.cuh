@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
     // clip before the one they wait for has been consumed), so an epilogue warp never waits on a resource that only it can
     // release.
     const bool is_epi = warp >= FW;
-    const int qd = is_epi ? warp - FW : 0;                  // TMEM quadrant == warp % 4 (FW is a multiple of 4)
+    const int qd = warp & 3;                                // TMEM quadrant = warp % 4: the four epilogue warps are consecutive, so all four occur
     // frame of (quadrant, lane): with deltas every quadrant carries a halo of n_deltas frames on either side (TMEM rows of
     // two quadrants overlap in time), so that np.gradient's neighbours are always lanes of the same warp
     const int halo = p.n_deltas, own = 32 - 2 * halo;
