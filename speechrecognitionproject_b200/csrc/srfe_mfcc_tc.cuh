@@ -2,7 +2,7 @@
 //
 // One persistent 16-warp CTA per SM, warp-specialised, NO CTA-wide barrier in steady state:
 //
-//   every warp                   (the epilogue warps only while they have nothing to finish) claims frame PAIRS from a shared-memory counter (a warp takes two, one per half-warp) and
+//   frame warps (0 .. FW-1)      claim frame PAIRS from a shared-memory counter (a warp takes two, one per half-warp) and
 //                                run the packed half-warp FFT -> power -> sparse Slaney sums -> log2 of srfe_kernels.cuh;
 //                                the (frame A, frame B) mel rows go into a RING of pair rows in shared memory
 //                                (capacity ~2 clips), followed by an atomic max (clip-wide top_db reference) and an
@@ -38,7 +38,7 @@ constexpr int kTcEpiWarps = 4;
 constexpr int kTcSlots = 4;                  // clips whose counters can be live at once (ring < 2 clips => 3 suffice)
 
 // control block in shared memory (ints)
-enum TcCtrl { TC_NEXT = 0, TC_CONSUMED = 1, TC_DONE = 2, TC_GMAX = 6, TC_S1 = 10, TC_TMEM = 14, TC_BAR = 16 /* 8-byte mbarrier */, TC_WORDS = 20 };
+enum TcCtrl { TC_NEXT = 0, TC_CONSUMED = 1, TC_DONE = 2, TC_GMAX = 6, TC_S1 = 10, TC_TMEM = 14, TC_BAR = 16 /* two 8-byte mbarriers */, TC_WORDS = 20 };
 
 __device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int tc_fkey(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }   // order-preserving
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
         ctrl[TC_NEXT] = 0; ctrl[TC_CONSUMED] = 0;
         for (int s = 0; s < kTcSlots; ++s) { ctrl[TC_DONE + s] = 0; ctrl[TC_GMAX + s] = (int)0x80000000; ctrl[TC_S1 + s] = 0; }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == FW) {                                       // this warp owns the TMEM allocation (and frees it at the end)
@@ -139,10 +140,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
     const int P = (p.T + 1) >> 1;                                                        // frame pairs per clip
     const int total = nc * P;
 
-    // Every warp runs the frame loop below; the four epilogue warps (FW .. FW+3, one per TMEM quadrant) first put every
-    // COMPLETE clip through the epilogue, and join the frame work only for pairs whose ring rows are free already (every
-    // clip before the one they wait for has been consumed), so an epilogue warp never waits on a resource that only it can
-    // release.
+    // The four epilogue warps (FW .. FW+3, one per TMEM quadrant) put every COMPLETE clip through the epilogue and sleep in
+    // between.  Letting them claim frame pairs while idle was built and measured (B200, clock64 build): they then run about
+    // one pair iteration per clip each, yet C-MFCC drops from 15.0 to 14.1 M clips/s -- twelve frame warps already hold the
+    // shared-memory pipe at ~75 % of its peak, extra frame warps only add contention (and delay the epilogues they owe).
     const bool is_epi = warp >= FW;
     const int qd = warp & 3;                                // TMEM quadrant = warp % 4: the four epilogue warps are consecutive, so all four occur
     // frame of (quadrant, lane): with deltas every quadrant carries a halo of n_deltas frames on either side (TMEM rows of
@@ -153,15 +154,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
     const bool towned = lane >= halo && lane < 32 - halo && t < p.T;
     const int n = p.n_filt, half = n >> 1;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * qd) << 16);
-    // TMEM columns: A operand s_hi | s_lo | d_hi | d_lo (n/2 each), then 3 accumulators per parity (one per product, summed
-    // in stage 2): back-to-back MMAs into ONE accumulator serialise on the MMA pipeline latency, six chains interleave
-    const uint32_t col_sh = 0, col_sl = half, col_dh = 2 * half, col_dl = 3 * half, col_de = 4 * half, col_do = 4 * half + 3 * p.tc_ne;
+    // TMEM columns: A operand s_hi | s_lo | d_hi | d_lo (n/2 each), then the accumulators (even | odd coefficients), TWO sets
+    // alternating with the clip: the MMAs of clip c run while stage 2 reads clip c-1's set
+    const uint32_t col_sh = 0, col_sl = half, col_dh = 2 * half, col_dl = 3 * half, col_acc = 4 * half, acc_cols = p.tc_ne + p.tc_no;
     const int R = (1 + p.n_deltas) * p.n_mfcc;
+    auto bar_of = [&](int clip) { return bar + 8u * (uint32_t)(clip & 1); };   // MMA-complete barriers, one per accumulator set
+    float c_prev = 0.f;                                     // centre of this thread's frame in the clip whose stage 2 is pending
+
+    // ---- stage 2 of clip cj (its MMAs are complete): coefficients of this thread's frame, deltas through warp shuffles,
+    //      straight to global memory ----
+    auto stage2 = [&](int cj, float cc) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* oc = p.out + (long long)((int)blockIdx.x + cj * (int)gridDim.x) * R * p.T;
+        // element (row r = d n_mfcc + k, frame t): FT -> oc[r T + t] (coalesced across the warp's frames), TF -> oc[t R + r]
+        const int st_r = p.layout == SRFE_LAYOUT_FT ? p.T : 1;                       // stride between rows
+        float* ot = oc + (p.layout == SRFE_LAYOUT_FT ? t : t * R);
+        // A deliberately ROLLED loop, one even and one odd coefficient per trip: the epilogue's code is cold every time
+        // it runs (the frame warps stream ~100 KB of unrolled FFT code through the instruction caches in between),
+        // and an unrolled version of this stage measured 5-8x slower on instruction fetch alone.
+        const int st_d = p.n_mfcc * st_r;
+        const uint32_t de = lane_base + col_acc + (cj & 1) * acc_cols, dox = de + p.tc_ne;
+        const float c0fix = cc * p.dct_row0_sum;                                     // put the frame's centre back on c0
+#pragma unroll 1
+        for (int j = 0; 2 * j < p.n_mfcc; ++j) {          // (4 + 4 coefficients per trip measured slower: more code to fetch)
+            const uint32_t e0 = tc_ld1_issue(de + j), o0 = tc_ld1_issue(dox + j);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float ve = __uint_as_float(e0), vo = __uint_as_float(o0);
+            if (j == 0) ve += c0fix;
+            const bool odd_ok = 2 * j + 1 < p.n_mfcc;
+            float* o = ot + 2 * j * st_r;                                           // rows k = 2 j and 2 j + 1
+            if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
+#pragma unroll 1
+            for (int d = 1; d <= p.n_deltas; ++d) {
+                // np.gradient along time (unit spacing, edge_order 1): neighbours are lanes of this warp
+                const float ue = __shfl_down_sync(0xffffffffu, ve, 1), le = __shfl_up_sync(0xffffffffu, ve, 1);
+                const float uo = __shfl_down_sync(0xffffffffu, vo, 1), lo = __shfl_up_sync(0xffffffffu, vo, 1);
+                ve = t <= 0 ? ue - ve : (t >= p.T - 1 ? ve - le : 0.5f * (ue - le));
+                vo = t <= 0 ? uo - vo : (t >= p.T - 1 ? vo - lo : 0.5f * (uo - lo));
+                o += st_d;
+                if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
 
     int ci = 0;                                             // epilogue warps: the next clip to finish
 #ifdef SRFE_DEV
-    long long tk_s1 = 0, tk_sync = 0, tk_mma = 0, tk_s2 = 0, tk_help = 0, tk_idle = 0, tk_mark = clock64(), tk_t0 = tk_mark;
-    int n_help = 0;
+    long long tk_s1 = 0, tk_sync = 0, tk_mma = 0, tk_s2 = 0, tk_idle = 0, tk_mark = clock64(), tk_t0 = tk_mark;
 #define SRFE_TICK(acc) do { const long long now__ = clock64(); acc += now__ - tk_mark; tk_mark = now__; } while (0)
 #else
 #define SRFE_TICK(acc) do { } while (0)
@@ -172,11 +211,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
         if (is_epi) {
             bool quit = false;
             for (;;) {
-                if (ci == nc) { quit = true; break; }
+                if (ci == nc) {                           // all clips through stage 1: the last one's stage 2 is still pending
+                    tc_mbar_wait(bar_of(nc - 1), (uint32_t)(((nc - 1) >> 1) & 1));
+                    stage2(nc - 1, c_prev);
+                    quit = true;
+                    break;
+                }
                 const int slot = ci & (kTcSlots - 1);
                 if (ctrl[TC_DONE + slot] >= P) {
                     SRFE_TICK(tk_idle);
                     __threadfence_block();                                        // every pair of the clip is in the ring
+                    // the A operand is single-buffered: the previous clip's MMAs must have read it (they have had a whole
+                    // clip period; this wait is normally free) -- which also makes that clip's accumulators final
+                    if (ci > 0) tc_mbar_wait(bar_of(ci - 1), (uint32_t)(((ci - 1) >> 1) & 1));
+                    SRFE_TICK(tk_mma);
                     const float gmax = tc_funkey(ctrl[TC_GMAX + slot]);
                     const float thr = p.top_db >= 0.f ? gmax - p.top_db : -CUDART_INF_F;     // power_to_db(top_db), log2 units
                     // ---- stage 1: ring row -> clamp, re-centre, fold, split -> TMEM A operand ----
@@ -222,20 +270,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
                             // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
                             const uint32_t id_e = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_ne >> 3) << 17) | ((128u >> 4) << 24);
                             const uint32_t id_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.tc_no >> 3) << 17) | ((128u >> 4) << 24);
-                            for (int ks = 0; ks < half / 8; ++ks) {
+                            const uint32_t dset = tmem + col_acc + (ci & 1) * acc_cols;
 #pragma unroll
-                                for (int par = 0; par < 2; ++par) {
-                                    const uint32_t b_hi = sb + (par ? 2 * be_bytes : 0), b_lo = b_hi + (par ? bo_bytes : be_bytes);
-                                    const uint32_t a_hi = tmem + (par ? col_dh : col_sh), a_lo = tmem + (par ? col_dl : col_sl);
-                                    const uint32_t nn = par ? p.tc_no : p.tc_ne, dcol = tmem + (par ? col_do : col_de), idesc = par ? id_o : id_e;
+                            for (int par = 0; par < 2; ++par) {
+                                const uint32_t b_hi = sb + (par ? 2 * be_bytes : 0), b_lo = b_hi + (par ? bo_bytes : be_bytes);
+                                const uint32_t a_hi = tmem + (par ? col_dh : col_sh), a_lo = tmem + (par ? col_dl : col_sl);
+                                const uint32_t dcol = dset + (par ? p.tc_ne : 0), idesc = par ? id_o : id_e;
+                                uint32_t acc = 0;
 #pragma unroll
-                                    for (int pr = 0; pr < 3; ++pr) {    // hi hi, lo hi, hi lo -> accumulators 0, 1, 2
-                                        const uint32_t a = pr == 1 ? a_lo : a_hi, b = pr == 2 ? b_lo : b_hi;
-                                        tc_mma_tf32(dcol + pr * nn, a + 8 * ks, tc_desc(b + ks * 2 * lbo, lbo, sbo), idesc, ks > 0);
+                                for (int pr = 0; pr < 3; ++pr) {        // hi hi + lo hi + hi lo, one accumulator
+                                    const uint32_t a = pr == 1 ? a_lo : a_hi, b = pr == 2 ? b_lo : b_hi;
+                                    for (int ks = 0; ks < half / 8; ++ks) {
+                                        tc_mma_tf32(dcol, a + 8 * ks, tc_desc(b + ks * 2 * lbo, lbo, sbo), idesc, acc);
+                                        acc = 1;
                                     }
                                 }
                             }
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_of(ci)) : "memory");
                             // the clip's ring rows and counters are free again (nobody reads them after stage 1)
                             ctrl[TC_S1 + slot] = 0; ctrl[TC_DONE + slot] = 0; ctrl[TC_GMAX + slot] = (int)0x80000000;
                             __threadfence_block();
@@ -243,66 +294,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
                         }
                         __syncwarp();
                     }
-                    // ---- stage 2: coefficients of this thread's frame, deltas through warp shuffles, straight to global ----
                     SRFE_TICK(tk_sync);
-                    tc_mbar_wait(bar, (uint32_t)(ci & 1));
-                    SRFE_TICK(tk_mma);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    float* oc = p.out + (long long)((int)blockIdx.x + ci * (int)gridDim.x) * R * p.T;
-                    // element (row r = d n_mfcc + k, frame t): FT -> oc[r T + t] (coalesced across the warp's frames), TF -> oc[t R + r]
-                    const int st_r = p.layout == SRFE_LAYOUT_FT ? p.T : 1;                       // stride between rows
-                    float* ot = oc + (p.layout == SRFE_LAYOUT_FT ? t : t * R);
-                    // A deliberately ROLLED loop, one even and one odd coefficient per trip: the epilogue's code is cold every time
-                    // it runs (the frame warps stream ~100 KB of unrolled FFT code through the instruction caches in between),
-                    // and an unrolled version of this stage measured 5-8x slower on instruction fetch alone.
-                    const int st_d = p.n_mfcc * st_r;
-                    const uint32_t de = lane_base + col_de, dox = lane_base + col_do;
-                    const float c0fix = c * p.dct_row0_sum;                                      // put the frame's centre back on c0
-#pragma unroll 1
-                    for (int j = 0; 2 * j < p.n_mfcc; ++j) {      // (4 + 4 coefficients per trip measured slower: more code to fetch)
-                        const uint32_t e0 = tc_ld1_issue(de + j), e1 = tc_ld1_issue(de + p.tc_ne + j), e2 = tc_ld1_issue(de + 2 * p.tc_ne + j);
-                        const uint32_t o0 = tc_ld1_issue(dox + j), o1 = tc_ld1_issue(dox + p.tc_no + j), o2 = tc_ld1_issue(dox + 2 * p.tc_no + j);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        float ve = (__uint_as_float(e0) + __uint_as_float(e1)) + __uint_as_float(e2);
-                        float vo = (__uint_as_float(o0) + __uint_as_float(o1)) + __uint_as_float(o2);
-                        if (j == 0) ve += c0fix;
-                        const bool odd_ok = 2 * j + 1 < p.n_mfcc;
-                        float* o = ot + 2 * j * st_r;                                           // rows k = 2 j and 2 j + 1
-                        if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
-#pragma unroll 1
-                        for (int d = 1; d <= p.n_deltas; ++d) {
-                            // np.gradient along time (unit spacing, edge_order 1): neighbours are lanes of this warp
-                            const float ue = __shfl_down_sync(0xffffffffu, ve, 1), le = __shfl_up_sync(0xffffffffu, ve, 1);
-                            const float uo = __shfl_down_sync(0xffffffffu, vo, 1), lo = __shfl_up_sync(0xffffffffu, vo, 1);
-                            ve = t <= 0 ? ue - ve : (t >= p.T - 1 ? ve - le : 0.5f * (ue - le));
-                            vo = t <= 0 ? uo - vo : (t >= p.T - 1 ? vo - lo : 0.5f * (uo - lo));
-                            o += st_d;
-                            if (towned) { o[0] = ve; if (odd_ok) o[st_r] = vo; }
-                        }
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    // ---- stage 2 of the PREVIOUS clip, while this clip's MMAs run ----
+                    if (ci > 0) stage2(ci - 1, c_prev);
+                    c_prev = c;
                     SRFE_TICK(tk_s2);
                     ++ci;
                     continue;
                 }
-                int got = 0;
-                if (lane == 0) {
-                    const int nx = ctrl[TC_NEXT];
-                    if (nx + 2 <= min(ci * P + RING, total)) { got = atomicCAS(const_cast<int*>(&ctrl[TC_NEXT]), nx, nx + 2) == nx; g0 = nx; }
-                }
-                got = __shfl_sync(0xffffffffu, got, 0);
-                if (got) break;
                 __nanosleep(100);
             }
             SRFE_TICK(tk_idle);
 #ifdef SRFE_DEV
-            if (quit && blockIdx.x == 0 && lane == 0)
-                printf("epi warp %d: clips %d cycles/clip: total %lld idle %lld stage1 %lld sync+issue %lld mma-wait %lld stage2 %lld help %lld (%d iterations)\n",
-                       qd, nc, (clock64() - tk_t0) / nc, tk_idle / nc, tk_s1 / nc, tk_sync / nc, tk_mma / nc, tk_s2 / nc, tk_help / nc, n_help);
-            if (!quit) ++n_help;
+            if (blockIdx.x == 0 && lane == 0)
+                printf("epi warp %d: clips %d cycles/clip: total %lld idle %lld stage1 %lld sync+issue %lld a-operand wait %lld stage2 %lld\n",
+                       qd, nc, (clock64() - tk_t0) / nc, tk_idle / nc, tk_s1 / nc, tk_sync / nc, tk_mma / nc, tk_s2 / nc);
 #endif
-            if (quit) break;
-            g0 = __shfl_sync(0xffffffffu, g0, 0);
+            (void)quit;
+            break;                                          // the epilogue warps never run frame pairs (see header comment)
         } else {
             if (lane == 0) g0 = atomicAdd(const_cast<int*>(&ctrl[TC_NEXT]), 2);
             g0 = __shfl_sync(0xffffffffu, g0, 0);
@@ -361,9 +370,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
             __threadfence_block();                      // row, mean and max before the count
             atomicAdd(const_cast<int*>(&ctrl[TC_DONE + (pc & (kTcSlots - 1))]), 1);
         }
-#ifdef SRFE_DEV
-        if (is_epi) SRFE_TICK(tk_help);
-#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
