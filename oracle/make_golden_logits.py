@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Golden logits of the UNMODIFIED reference model models/model_mfcc_bgru.py (TEST INFRASTRUCTURE ONLY; runs in the
+"""Golden logits of the UNMODIFIED reference models models/model_{mfcc_bgru,spec_bgru,spec_cnn,fbanks_cnn}.py (TEST INFRASTRUCTURE ONLY; runs in the
 build container where /root/reference is mounted).
 
-    python oracle/make_golden_logits.py      # writes tests/golden/model_mfcc_bgru_logits.npz
+    python oracle/make_golden_logits.py      # writes tests/golden/<model>_logits.npz
 
 torch.manual_seed(SEED); Network() (full size: GRU(39, 512, 2 layers, bidirectional) + Linear(1024, 12),
 models/model_mfcc_bgru.py:23-26); Network.forward (:28-37, the per-clip CPU loop over compute_mfcc, librosa through
@@ -32,17 +32,18 @@ def param_checksums(net) -> dict:
 
 
 def main() -> None:
-    mod = twins.load_reference("model_mfcc_bgru")
-    torch.manual_seed(SEED)
-    net = mod.Network().eval()
     x = oracle.synthetic_corpus(N_CLIPS, config_index=CONFIG_INDEX)
-    with torch.no_grad():
-        logits = net(torch.from_numpy(x)).numpy()
-    cs = param_checksums(net)
-    out = os.path.join(ROOT, "tests", "golden", "model_mfcc_bgru_logits.npz")
-    np.savez_compressed(out, seed=SEED, n_clips=N_CLIPS, config_index=CONFIG_INDEX, logits=logits,
-                        keys=np.array(list(cs.keys())), checksums=np.stack(list(cs.values())))
-    print("wrote", out, logits.shape, float(np.abs(logits).max()))
+    for name in twins.TWINNED:
+        mod = twins.load_reference(name)
+        torch.manual_seed(SEED)
+        net = mod.Network().eval()
+        with torch.no_grad():
+            logits = net(torch.from_numpy(x)).numpy()
+        cs = param_checksums(net)
+        out = os.path.join(ROOT, "tests", "golden", f"{name}_logits.npz")
+        np.savez_compressed(out, seed=SEED, n_clips=N_CLIPS, config_index=CONFIG_INDEX, logits=logits,
+                            keys=np.array(list(cs.keys())), checksums=np.stack(list(cs.values())))
+        print("wrote", out, logits.shape, float(np.abs(logits).max()))
 
 
 if __name__ == "__main__":

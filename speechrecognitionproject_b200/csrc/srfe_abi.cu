@@ -825,11 +825,19 @@ static void gather_rows(char* dst, const char* src, size_t rows, size_t row_byte
     if (nthr == 1) { work(0, rows); return; }
     std::vector<std::thread> th;
     const size_t per = (rows + nthr - 1) / nthr;
+    size_t done_to = std::min(rows, per);                  // rows [0, per) are the calling thread's
     for (unsigned t = 1; t < nthr; ++t) {
         const size_t r0 = std::min(rows, t * per), r1 = std::min(rows, r0 + per);
-        if (r0 < r1) th.emplace_back(work, r0, r1);
+        if (r0 >= r1) break;
+        try {
+            th.emplace_back(work, r0, r1);
+        } catch (...) {                                    // no more threads to be had: the caller copies the rest itself
+            break;
+        }
+        done_to = r1;
     }
     work(0, std::min(rows, per));
+    if (done_to < rows) work(done_to, rows);
     for (auto& t : th) t.join();
 }
 

@@ -59,11 +59,14 @@ __global__ void __launch_bounds__(256) srfe_augment_kernel(const AugParams p) {
     if (p.n_files > 0) {
         const int f = aug_scaled(r.y, (unsigned)p.n_files);
         const long long b0 = p.bank_off[f], len = p.bank_off[f + 1] - b0;
-        nz = p.bank + b0 + aug_scaled(r.z, (unsigned)(len - N + 1));
-    }
+        if (len >= N) nz = p.bank + b0 + aug_scaled(r.z, (unsigned)(len - N + 1));      // (a file shorter than a clip violates the
+    }                                                                                   //  contract: its ops degrade to a copy)
     const float u = aug_u01(r.x);
     int op = SRFE_AUG_NONE;
-    if (kind == 1) {
+    if (nz == nullptr && (kind == 2 || (u >= p.noise_lo && u < p.noise_hi) || (u >= p.snr_lo && u < p.snr_hi))) {
+        for (int j = tid; j < N; j += blockDim.x) o[j] = kind == 2 ? 0.f : (float)s[j];
+        op = kind == 2 ? SRFE_AUG_SILENCE_ZERO : SRFE_AUG_NONE;
+    } else if (kind == 1) {
         op = SRFE_AUG_SILENCE_ZERO;
         for (int j = tid; j < N; j += blockDim.x) o[j] = 0.f;
     } else if (kind == 2) {

@@ -278,9 +278,12 @@ def test_shared_front_end_gpu(srfe_lib):
         patch.unpatch_model(m)
 
 
-# ---- the full-size model_mfcc_bgru (BASELINE cfg5) pinned to the UNMODIFIED reference module -----------------------
-def _golden_logits():
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_mfcc_bgru_logits.npz"))
+# ---- the full-size reference models pinned to the UNMODIFIED reference modules (model_mfcc_bgru = BASELINE cfg5) ----
+MODELS = ["model_mfcc_bgru", "model_spec_bgru", "model_spec_cnn", "model_fbanks_cnn"]
+
+
+def _golden_logits(name="model_mfcc_bgru"):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}_logits.npz"))
     return {k: g[k] for k in g.files}
 
 
@@ -297,41 +300,44 @@ def _assert_checksums(net, g):
         np.testing.assert_allclose([float(v.sum()), float(v.abs().sum())], want, rtol=1e-12, atol=0, err_msg=str(k))   # sums re-associate across CPUs
 
 
+@pytest.mark.parametrize("name", MODELS)
 @pytest.mark.filterwarnings("ignore")
-def test_twin_regenerates_the_reference_weights_and_logits():
-    """tests/twins.py's shape twin, seeded like oracle/make_golden_logits.py seeded the unmodified reference module,
-    has the reference's parameters bit for bit (per-tensor checksums recorded from the real module) and its forward
+def test_twin_regenerates_the_reference_weights_and_logits(name):
+    """tests/twins.py's shape twins, seeded like oracle/make_golden_logits.py seeded the unmodified reference modules,
+    have the reference's parameters (per-tensor checksums recorded from the real modules) and their forward
     (per-clip CPU loop, oracle features) returns the recorded reference logits."""
     from tests import twins
-    g = _golden_logits()
-    net = _seeded_net(twins.twin_model_mfcc_bgru(), g["seed"])
+    g = _golden_logits(name)
+    net = _seeded_net(twins.twin(name), g["seed"])
     _assert_checksums(net, g)
     x = torch.from_numpy(oracle.synthetic_corpus(int(g["n_clips"]), config_index=int(g["config_index"])))
     with torch.no_grad():
-        np.testing.assert_allclose(net(x).numpy(), g["logits"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(net(x).numpy(), g["logits"], rtol=0, atol=2e-5)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("name", MODELS)
 @pytest.mark.filterwarnings("ignore")
-def test_twin_equals_reference_module():
+def test_twin_equals_reference_module(name):
     from tests import twins
-    g = _golden_logits()
-    ref = _seeded_net(twins.load_reference("model_mfcc_bgru"), g["seed"])
-    twin = _seeded_net(twins.twin_model_mfcc_bgru(), g["seed"])
+    g = _golden_logits(name)
+    ref = _seeded_net(twins.load_reference(name), g["seed"])
+    twin = _seeded_net(twins.twin(name), g["seed"])
     _assert_checksums(ref, g)
     for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), twin.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", MODELS)
 @pytest.mark.filterwarnings("ignore")
-def test_full_size_model_mfcc_bgru_gpu_vs_reference_logits(srfe_lib):
-    """cfg5's model at full size on the GPU: reference weights (regenerated from the seed, checksummed), forward
-    re-plumbed by patch_model (PCM H2D -> fused MFCC kernel -> cuDNN BGRU), logits against the ones the UNMODIFIED
-    reference module produced on the CPU (tests/golden/model_mfcc_bgru_logits.npz)."""
+def test_full_size_reference_models_gpu_vs_reference_logits(srfe_lib, name):
+    """The reference's networks at full size on the GPU: reference weights (regenerated from the seed, checksummed),
+    forward re-plumbed by patch_model (PCM H2D -> fused feature kernel -> the model's own layers), logits against the
+    ones the UNMODIFIED reference module produced on the CPU (tests/golden/<model>_logits.npz)."""
     from tests import twins
-    g = _golden_logits()
-    mod, which = twins.load("model_mfcc_bgru")
+    g = _golden_logits(name)
+    mod, which = twins.load(name)
     net = _seeded_net(mod, g["seed"])
     _assert_checksums(net, g)
     net = net.cuda()
@@ -342,8 +348,13 @@ def test_full_size_model_mfcc_bgru_gpu_vs_reference_logits(srfe_lib):
             got = net(x)
             got_dev = net(x.cuda())
         assert got.is_cuda and torch.equal(got, got_dev)
-        # features differ from the CPU path by <= 1e-3 (MFCC tolerance), which moves these logits by < 1e-5 (measured);
-        # TF32 is off for cuDNN RNNs by default
-        np.testing.assert_allclose(got.cpu().numpy(), g["logits"], rtol=0, atol=2e-4, err_msg=which)
+        err = float(np.abs(got.cpu().numpy() - g["logits"]).max())
+        print(f"\n{name} ({which}): max abs logit difference vs the unmodified reference module {err:.2e}")
+        # MFCC features differ from the CPU path by <= 1e-3 everywhere, which moves the BGRU logits by < 1e-5 (measured);
+        # the log-spectrogram / log-fbank models also see the deep-null elements outside the tolerance domain
+        # (tests/tolerances.py), through randomly initialised convolutions: bounded loosely, printed exactly.
+        # TF32 is off for cuDNN RNNs and convolutions by default.
+        tol = 2e-4 if name == "model_mfcc_bgru" else 2e-2 * max(1.0, float(np.abs(g["logits"]).max()))
+        assert err <= tol, (name, which, err)
     finally:
         patch.unpatch_model(mod)
