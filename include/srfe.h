@@ -218,6 +218,13 @@ int srfe_augment_i16(const int16_t* pcm, int64_t n_clips, int64_t n_samples, int
                      int64_t first_clip_index, const int16_t* noise_bank, const int64_t* noise_offsets, int32_t n_noise_files,
                      const srfe_augment_params* p, float* out, int8_t* op_out, void* cuda_stream);
 
+/* Host rows -> a DEVICE buffer the caller owns, stream-ordered on `cuda_stream` of `device`: the PCM upload of the
+ * reference's forward (`x.to(DEVICE)` of a DataLoader batch, pageable: training.py:77) through libsrfe's pinned staging ring
+ * and copy threads instead of the driver's single staged copy; pinned sources are copied directly.  `dev` receives the rows
+ * densely packed (row_bytes apart).  Returns once the host buffer may be reused. */
+int srfe_upload(const void* host, int64_t rows, int64_t row_bytes, int64_t row_stride_bytes, void* dev, int device,
+                void* cuda_stream);
+
 /* frees the host entry points' per-device workspaces (streams, device buffers, pinned staging); they are re-created on
  * the next host call.  Returns SRFE_OK. */
 int srfe_release_host_workspace(void);

@@ -10,7 +10,7 @@ from .features import (  # noqa: F401
     SpecParams, FbankParams, MfccParams, PRESETS,
     R_SPEC, C_SPEC, R_FBANK, C_FBANK, R_MFCC, C_MFCC, C_MFCC_D2,
     spec, fbank, mfcc, spec_fbank, compute_spec, filter_banks, compute_mfcc,
-    out_shape, bytes_per_clip, launch_count, set_tuning, release_host_workspace,
+    out_shape, bytes_per_clip, launch_count, set_tuning, release_host_workspace, to_device,
 )
 from .patch import patch_model, SharedFrontEnd  # noqa: F401
 

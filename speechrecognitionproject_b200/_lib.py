@@ -50,6 +50,7 @@ SYMBOLS = {
     "srfe_device_count": (_i32, []),
     "srfe_launch_count": (_i64, []),
     "srfe_release_host_workspace": (_i32, []),
+    "srfe_upload": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _vp]),
     "srfe_spec_fbank_f32": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), C.POINTER(FbankParamsC), _vp, _vp, _vp]),
     "srfe_spec_fbank_i16": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(SpecParamsC), C.POINTER(FbankParamsC), _vp, _vp, _vp]),
     "srfe_augment_i16": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i32, C.POINTER(AugmentParamsC), _vp, _vp, _vp]),

@@ -903,6 +903,55 @@ static int run_host(int family, const void* pcm, bool i16, int64_t n_clips, int6
     return rc;
 }
 
+// Host rows -> a device buffer the caller owns, through the same pinned staging ring (pageable sources) or directly
+// (pinned sources), stream-ordered on `st`: what `x.to(device)` does in the reference's forward, at PCIe speed instead
+// of the driver's single staged copy.  The staging buffers are reused chunk by chunk, so the gathers run on the calling
+// thread while earlier chunks are in flight; the function returns when the last chunk has been handed to the copy engine
+// and its staging buffer may be reused (the device side completes in stream order).
+static int upload_rows(const void* host, int64_t rows, int64_t row_bytes, int64_t row_stride_bytes, void* dev, int device, cudaStream_t st) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return fail(SRFE_ERR_NO_DEVICE, "no CUDA device"); }
+    if (device < 0 || device >= kMaxDevices) return fail(SRFE_ERR_BAD_ARG, "device index out of range");
+    if (rows == 0) return SRFE_OK;
+    SRFE_CUDA(cudaSetDevice(device));
+    int rc = SRFE_OK;
+    if (!is_pageable(host)) {
+        cudaError_t ce = cudaMemcpy2DAsync(dev, (size_t)row_bytes, host, (size_t)row_stride_bytes, (size_t)row_bytes, (size_t)rows, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "H2D");
+        cudaSetDevice(prev);
+        return rc;
+    }
+    HostWs& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)((32u << 20) / (size_t)row_bytes)));
+    rc = host_ws_prepare(w, 0, 0, false, false);
+    if (rc == SRFE_OK) rc = grow_pair(w.h_in, w.cap_hin, (size_t)chunk * row_bytes, [](void** q, size_t n) { return cudaMallocHost(q, n); },
+                                      [](void* q) { cudaFreeHost(q); }, "cudaMallocHost (input staging)");
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2 && rc == SRFE_OK; ++i) {
+        cudaError_t ce = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaEventCreate");
+    }
+    bool used[2] = {false, false};
+    for (int64_t r0 = 0, i = 0; rc == SRFE_OK && r0 < rows; r0 += chunk, ++i) {
+        const int64_t nr = std::min(chunk, rows - r0);
+        const int s2 = (int)(i & 1);
+        if (used[s2]) { cudaError_t ce = cudaEventSynchronize(ev[s2]); if (ce != cudaSuccess) { rc = cuda_fail(ce, "cudaEventSynchronize"); break; } }
+        gather_rows((char*)w.h_in[s2], (const char*)host + (size_t)r0 * row_stride_bytes, (size_t)nr, (size_t)row_bytes, (size_t)row_stride_bytes);
+        cudaError_t ce = cudaMemcpyAsync((char*)dev + (size_t)r0 * row_bytes, w.h_in[s2], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[s2], st);
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D"); break; }
+        used[s2] = true;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!ev[i]) continue;
+        if (used[i]) { cudaError_t ce = cudaEventSynchronize(ev[i]); if (ce != cudaSuccess && rc == SRFE_OK) rc = cuda_fail(ce, "cudaEventSynchronize"); }
+        cudaEventDestroy(ev[i]);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
 static int release_host_ws() {
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return SRFE_OK; }     // no device: nothing was allocated
@@ -945,6 +994,11 @@ int srfe_device_count(void) {
 }
 int64_t srfe_launch_count(void) { return g_launches.load(); }
 int srfe_release_host_workspace(void) { return release_host_ws(); }
+int srfe_upload(const void* host, int64_t rows, int64_t row_bytes, int64_t row_stride_bytes, void* dev, int device, void* stream) {
+    if (rows < 0 || row_bytes <= 0 || row_stride_bytes < row_bytes) return fail(SRFE_ERR_BAD_ARG, "upload: bad sizes");
+    if (rows > 0 && (!host || !dev)) return fail(SRFE_ERR_BAD_ARG, "upload: host/dev is NULL");
+    return upload_rows(host, rows, row_bytes, row_stride_bytes, dev, device, (cudaStream_t)stream);
+}
 
 static int spec_fbank(const void* pcm, bool i16, int64_t n_clips, int64_t n_samples, int64_t clip_stride, const srfe_spec_params* ps,
                       const srfe_fbank_params* pf, float* out_spec, float* out_fbank, void* stream) {

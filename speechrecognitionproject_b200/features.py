@@ -32,7 +32,7 @@ __all__ = [
     "SpecParams", "FbankParams", "MfccParams", "PRESETS",
     "R_SPEC", "C_SPEC", "R_FBANK", "C_FBANK", "R_MFCC", "C_MFCC", "C_MFCC_D2",
     "spec", "fbank", "mfcc", "spec_fbank", "compute_spec", "filter_banks", "compute_mfcc",
-    "out_shape", "bytes_per_clip", "launch_count", "set_tuning", "release_host_workspace",
+    "out_shape", "bytes_per_clip", "launch_count", "set_tuning", "release_host_workspace", "to_device",
 ]
 
 
@@ -149,6 +149,29 @@ def set_tuning(**knobs: int) -> None:
         knobs = {k: 0 for k in _TUNING_KNOBS}
     for k, v in knobs.items():
         _lib.check(_lib.lib().srfe_set_tuning(k.encode(), int(v)))
+
+
+def to_device(x: torch.Tensor, device=None) -> torch.Tensor:
+    """``x.to(device)`` for a CPU PCM batch ``[n_clips, n_samples]`` (float32 or int16), through ``srfe_upload``: pageable
+    tensors -- what the reference's DataLoader yields (training.py:77, no ``pin_memory``) -- go through libsrfe's pinned
+    staging ring with a few copy threads (2x torch's pageable copy on the B200 box), pinned ones straight over PCIe.
+    Stream-ordered on the current stream of ``device``; CUDA tensors are returned as they are."""
+    if x.is_cuda:
+        return x
+    if not torch.cuda.is_available():
+        raise RuntimeError("srfe: no CUDA device visible")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.float32, torch.int16):
+        return x.to(dev, non_blocking=True)
+    out = torch.empty(x.shape, dtype=x.dtype, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        es = x.element_size()
+        _lib.check(_lib.lib().srfe_upload(x.data_ptr(), x.size(0), x.size(1) * es, (x.stride(0) if x.size(0) > 1 else x.size(1)) * es,
+                                          out.data_ptr(), dev.index, stream))
+    return out
 
 
 def release_host_workspace() -> None:

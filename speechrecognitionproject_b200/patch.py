@@ -78,7 +78,7 @@ class SharedFrontEnd:
             self._src, self._version, self._dev = x, x._version, dev
             self._feat.clear()
             if x.device != dev:
-                self._pcm = x.to(dev, non_blocking=True)
+                self._pcm = F.to_device(x, dev) if dev.type == "cuda" else x.to(dev)
                 self.uploads += 1
             else:
                 self._pcm = x
@@ -165,8 +165,8 @@ def make_forward(kind: str, feature_fn: Optional[Callable] = None, frontend: Opt
                 f = frontend.features(_FEATURE_SET[kind], feat, x, dev)
                 x = frontend.pcm(x, dev)
             else:
-                if x.device != dev:
-                    x = x.to(dev, non_blocking=True)   # the only H2D: raw PCM
+                if x.device != dev:                    # the only H2D: raw PCM (pageable batches through libsrfe's staging ring)
+                    x = F.to_device(x, dev) if dev.type == "cuda" else x.to(dev)
                 f = feat(x)
         if f.device != dev:
             f = f.to(dev)

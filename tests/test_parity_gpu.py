@@ -630,3 +630,23 @@ def test_spectrogram_with_tma_staged_frames(srfe_lib, corpus):
             S.spec(x[:8], S.R_SPEC)
     finally:
         S.set_tuning()
+
+
+def test_upload_through_the_staging_ring(srfe_lib, corpus):
+    """srfe_upload / features.to_device: the reference forward's `x.to(DEVICE)` for pageable, pinned, strided and int16
+    batches; bytes arrive unchanged, stream-ordered."""
+    x = torch.from_numpy(np.concatenate([corpus] * 30))                      # 720 clips = 46 MB: several staging chunks
+    assert not x.is_pinned()
+    for src in (x, x.pin_memory(), x[:, :8000], x[::2], x.to(torch.int16), x[:1], x[:0]):
+        got = S.to_device(src)
+        assert got.is_cuda and got.dtype == src.dtype and got.shape == src.shape and got.is_contiguous()
+        assert torch.equal(got.cpu(), src)
+    y = S.to_device(x)
+    assert torch.equal(S.mfcc(y), S.mfcc(x.cuda()))
+    assert S.to_device(y) is y
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        z = S.to_device(x)
+        f = S.mfcc(z)
+    st.synchronize()
+    assert torch.equal(f, S.mfcc(y))
