@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
         const uint32_t de = lane_base + col_acc + (cj & 1) * acc_cols, dox = de + p.tc_ne;
         const float c0fix = cc * p.dct_row0_sum;                                     // put the frame's centre back on c0
 #pragma unroll 1
-        for (int j = 0; 2 * j < p.n_mfcc; ++j) {          // (4 + 4 coefficients per trip measured slower: more code to fetch)
-            const uint32_t e0 = tc_ld1_issue(de + j), o0 = tc_ld1_issue(dox + j);
+        for (int j = 0; 2 * j < p.n_mfcc; ++j) {          // (4 + 4 coefficients per trip, and issuing trip j + 1's loads under trip j,
+            const uint32_t e0 = tc_ld1_issue(de + j), o0 = tc_ld1_issue(dox + j);     //  both measured no faster: the cost is code fetch)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float ve = __uint_as_float(e0), vo = __uint_as_float(o0);
             if (j == 0) ve += c0fix;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
                     ++ci;
                     continue;
                 }
-                __nanosleep(100);
+                __nanosleep(1000);                          // ~2 k cycles: 4 polling warps at 100 ns were 8 % of all issued instructions
             }
             SRFE_TICK(tk_idle);
 #ifdef SRFE_DEV
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
         const int row = valid ? gg - (int)__umulhi((unsigned)gg, p.tc_ring_magic) * RING : RING;       // RING = dummy row
         if (valid && gg >= RING) {
             const int need = (int)__umulhi((unsigned)(gg - RING), p.tc_p_magic);                     // clip of pair gg - RING
-            while (ctrl[TC_CONSUMED] <= need) __nanosleep(64);
+            while (ctrl[TC_CONSUMED] <= need) __nanosleep(256);
             __threadfence_block();
         }
         P2* prow = tileP + row * TSP;
