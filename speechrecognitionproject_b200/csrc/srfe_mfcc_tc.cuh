@@ -8,8 +8,8 @@
 //                                (capacity ~2 clips), followed by an atomic max (clip-wide top_db reference) and an
 //                                atomic "pairs done" count per clip.  A CTA's clips form one continuous pair stream,
 //                                so there are no partly filled rounds at clip boundaries any more.
-//   epilogue warps (FW .. FW+3)  warp e owns TMEM lanes / frames 32 e .. 32 e + 31 (a warp can only address its own
-//                                quadrant).  Per clip, thread = frame:
+//   epilogue warps (FW .. FW+3)  warp w owns TMEM quadrant w % 4 (a warp can only address its own 32 lanes) = frames
+//                                32 q .. 32 q + 31 (28 q - 2 .. with two deltas).  Per clip, thread = frame:
 //        stage 1  row of 128 log2-mel values from the ring (conflict-free: one LDS per value), top_db clamp against
 //                 the clip maximum, re-centre on the frame mean, DCT-II symmetry fold s = x[f] + x[n-1-f],
 //                 d = x[f] - x[n-1-f], split into TF32 hi + lo, tcgen05.st into the A-operand columns of TMEM;
@@ -17,10 +17,10 @@
 //        MMA      one thread: [128 frames x n/2] . [n/2 x N] for even and odd coefficients, 3 products each
 //                 (hi hi + lo hi + hi lo = fp32-grade), kind::tf32, A from TMEM, B (folded DCT-II rows, hi / lo) from
 //                 shared memory (K-major, no swizzle), accumulators in TMEM; tcgen05.commit -> mbarrier
-//        stage 2  tcgen05.ld of the thread's coefficients (three partial accumulators summed), + c_t sqrt(n) on c0,
-//                 np.gradient deltas through warp shuffles (each quadrant carries a halo of n_deltas frames, so time
-//                 neighbours are always lanes of the same warp), straight to global memory: [k][t] rows are coalesced
-//                 across the warp's frames.
+//        stage 2  (of the PREVIOUS clip, under this clip's MMAs: the accumulators exist twice) tcgen05.ld of the thread's
+//                 coefficients, + c_t sqrt(n) on c0, np.gradient deltas through warp shuffles (each quadrant carries a
+//                 halo of n_deltas frames, so time neighbours are always lanes of the same warp), straight to global
+//                 memory: [k][t] rows are coalesced across the warp's frames.
 //
 // Parity: same arithmetic as the classic kernel up to the contraction (identical frame / mel code); the contraction's
 // 3xTF32 error is ~2^-22 relative per product on re-centred values (|x - c_t| < 30 log2 units).
