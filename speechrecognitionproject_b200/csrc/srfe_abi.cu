@@ -347,7 +347,7 @@ static int launch_tc(const KParams& kp, int dev, int grid, int smem_bytes, cudaS
 static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_out) {
     if (e->family != FAM_MFCC || e->tc_b_bytes == 0 || kp.T < 3 || kp.T > 4 * (32 - 2 * kp.n_deltas)) return false;
     auto up = [](int x, int a) { return (x + a - 1) / a * a; };
-    const int P = (kp.T + 1) / 2, nw = kTcThreads / 32;              // every warp (epilogue warps included) runs frame pairs
+    const int P = (kp.T + 1) / 2, nw = kTcThreads / 32 - kTcEpiWarps;   // FFT scratch for the frame warps only
     const int tmem_need = 2 * kp.n_filt + 2 * (e->tc_ne + e->tc_no);   // A operand (s / d, hi / lo) + two sets of accumulators
     if (tmem_need > 512) return false;
     int cols = 32;
