@@ -2,7 +2,7 @@
 tests cover the presets and a few generic shapes, this walks many more launch shapes and DCT tile choices)."""
 import sys, json
 import numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")      # run from the repo root: python tests/dev/<script>.py
 import oracle
 import speechrecognitionproject_b200 as S
 from tests import helpers as H

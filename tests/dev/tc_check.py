@@ -1,6 +1,6 @@
 """tcgen05 MFCC kernel vs the classic CUDA-core kernel and the oracle (dev tool; run under `timeout`)."""
 import sys, json, time, numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")      # run from the repo root: python tests/dev/<script>.py
 import oracle
 import speechrecognitionproject_b200 as S
 from dataclasses import replace
