@@ -231,8 +231,11 @@ int srfe_release_host_workspace(void);
 
 /* ---- introspection for benchmarks / tests --------------------------------- */
 /* Launch-shape override for tests and tuning sweeps: `name` in {"warps", "ctas", "cpc", "dct_cb", "dct_pq",
- * "mfcc_tc"}, value 0 = automatic (the default).  Results never depend on these (the parity suite checks it);
- * "mfcc_tc": 1 = force the classic CUDA-core MFCC kernel, 2 = require the tcgen05 one.  Process-wide, thread-safe. */
+ * "mfcc_tc", "stage", "fbank_tc"}, value 0 = automatic (the default).  Results never depend on these beyond the stated
+ * tolerance (the parity suite checks it); "mfcc_tc" / "fbank_tc": 1 = force the classic CUDA-core kernel of the family,
+ * 2 = require the tcgen05 one (SRFE_ERR_UNSUPPORTED when the parameter set does not fit it; the FBANK one is opt-in only:
+ * it ties the classic kernel and is not bit-identical to it); "stage": 2 = TMA-staged spectrogram frames.
+ * Process-wide, thread-safe. */
 int srfe_set_tuning(const char* name, int value);
 /* number of kernel launches issued by this process through the entry points */
 int64_t srfe_launch_count(void);

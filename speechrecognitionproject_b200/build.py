@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrfe.so")
 SOURCES = ["srfe_abi.cu", "srfe_tables.cpp"]
-HEADERS = ["srfe_kernels.cuh", "srfe_mfcc_tc.cuh", "srfe_augment.cuh", "srfe_fft.cuh", "srfe_tables.h", os.path.join("..", "..", "include", "srfe.h")]
+HEADERS = ["srfe_kernels.cuh", "srfe_mfcc_tc.cuh", "srfe_fbank_tc.cuh", "srfe_augment.cuh", "srfe_fft.cuh", "srfe_tables.h", os.path.join("..", "..", "include", "srfe.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC",
               # the CUDA runtime as a shared library (the one torch has already loaded, else the toolkit's): the artefact

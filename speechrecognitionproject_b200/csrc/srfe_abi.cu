@@ -20,6 +20,7 @@
 #include "../../include/srfe.h"
 #include "srfe_kernels.cuh"
 #include "srfe_mfcc_tc.cuh"
+#include "srfe_fbank_tc.cuh"
 #include "srfe_augment.cuh"
 #include "srfe_tables.h"
 
@@ -52,6 +53,7 @@ struct Entry {
     unsigned mel_code = 0;
     int n_bins = 0;
     int tc_b_off = 0, tc_b_bytes = 0, tc_ne = 0, tc_no = 0;   // tcgen05 MFCC path: DCT B operand in the blob (0 bytes = not eligible)
+    int ft_w_off = 0, ft_w_bytes = 0, ft_mid_slot = 0;         // tcgen05 FBANK path: filter weights as the MMA's A operand (0 bytes = not eligible)
 };
 
 struct Key {
@@ -194,7 +196,48 @@ static int build_entry(const srfe_fbank_params& p, Entry* e) {
     e->kp.start0 = 0;
     e->kp.preemph = p.preemph;
     e->kp.layout = SRFE_LAYOUT_TF;
-    return upload(e, bb);
+    const int classic_bytes = (int)bb.data.size();
+    // tcgen05 path (srfe_fbank_tc.cuh): the same fp32 weights as a dense [128 filters x 256] A operand, K-permuted the way
+    // the frame warps lay a frame's bins out (chunk c < 16: bins c + 16 e; 16 <= c < 32: bins 256 - (c - 16 + 16 e)), each
+    // weight split into bf16 hi + bf16 mid (round to nearest), two K elements per 32-bit TMEM column (even element in the
+    // low half): row = 128 hi words, then 128 mid words.  K = 256 = 16 MMA steps holds 256 of the 257 bins: bin 128 takes
+    // the slot of an edge bin that no filter weighs (bin 0 whenever the bank starts at 0 Hz -- a triangle is zero at its
+    // left foot -- else bin 256); a bank that weighs both edge bins stays on the classic kernel.
+    if (p.n_fft == 512 && p.nfilt <= 128) {
+        const int n_bins = p.n_fft / 2 + 1;
+        auto weightless = [&](int bin) {
+            for (int m = 0; m < p.nfilt; ++m) if (dense[(size_t)m * n_bins + bin] != 0.0) return false;
+            return true;
+        };
+        const int mid_slot = weightless(0) ? 0 : weightless(256) ? 1 : -1;
+        auto bf16_rn = [](float x) -> uint32_t {
+            uint32_t u; std::memcpy(&u, &x, 4);
+            return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;                 // finite inputs only
+        };
+        auto bf16_f = [](uint32_t h) -> float { const uint32_t u = h << 16; float x; std::memcpy(&x, &u, 4); return x; };
+        std::vector<uint32_t> wt((size_t)128 * kFtKP, 0u);
+        for (int m = 0; m < p.nfilt && mid_slot >= 0; ++m)
+            for (int kk = 0; kk < kFtKP; ++kk) {
+                const int c = kk / 8, el = kk % 8;
+                int bin = c < 16 ? c + 16 * el : 256 - ((c - 16) + 16 * el);
+                if (bin == (mid_slot == 0 ? 0 : 256)) bin = 128;
+                const float w = (float)(dense[(size_t)m * n_bins + bin] * (0.25 / (double)p.n_fft));   // the classic kernel's weight
+                const uint32_t hi = bf16_rn(w), mid = bf16_rn(w - bf16_f(hi));
+                const size_t row = (size_t)m * kFtKP;
+                wt[row + kk / 2] |= hi << (16 * (kk & 1));
+                wt[row + kFtKP / 2 + kk / 2] |= mid << (16 * (kk & 1));
+            }
+        if (mid_slot >= 0) {
+            while (bb.data.size() % 128) bb.data.push_back(0);
+            e->ft_w_bytes = (int)wt.size() * 4;
+            e->ft_w_off = bb.add(wt.data(), wt.size() * 4);
+            e->ft_mid_slot = mid_slot;
+        }
+    }
+    const int rc = upload(e, bb);
+    e->blob_smem = classic_bytes;                                          // what the classic kernel copies to shared memory
+    e->kp.blob_bytes = classic_bytes;
+    return rc;
 }
 
 static int build_entry(const srfe_mfcc_params& p, Entry* e) {
@@ -383,6 +426,45 @@ static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_ou
     return *smem_out <= di.smem_optin;
 }
 
+template <int JLO, int JHI, typename SAMP>
+static int launch_ft(const KParams& kp, int dev, int grid, int smem_bytes, cudaStream_t st) {
+    auto kern = srfe_fbank_tc_kernel<JLO, JHI, SAMP>;
+    static std::atomic<int> attr_set[kMaxDevices];
+    if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
+        SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int cur = attr_set[dev].load(std::memory_order_relaxed);
+        while (cur < smem_bytes && !attr_set[dev].compare_exchange_weak(cur, smem_bytes, std::memory_order_release)) {}
+    }
+    kern<<<grid, kFtThreads, smem_bytes, st>>>(kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "srfe_fbank_tc_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SRFE_OK;
+}
+
+// Shared-memory plan of the tcgen05 FBANK kernel: [FFT tables][FFT scratch of the frame warps][three 48-frame tile buffers]
+// [control block].  Returns false when the parameter set is not eligible (the classic kernel takes it).
+static bool plan_ft(const Entry* e, KParams& kp, const DevInfo& di, int* smem_out) {
+    if (e->family != FAM_FBANK || e->ft_w_bytes == 0 || e->n_fft != 512 || kp.T < 1) return false;
+    if ((double)kp.n_clips * ((kp.T + 1) / 2) >= 268435456.0) return false;              // pair-stream indices: ints, magic divisions
+    auto up = [](int x, int a) { return (x + a - 1) / a * a; };
+    const int P = (kp.T + 1) / 2, nw = kFtThreads / 32 - kTcEpiWarps;
+    kp.blob_bytes = up(kp.off_gm, 16);                                                   // FFT tables only (they precede the mel tables)
+    int off = up(kp.blob_bytes, 128);
+    kp.sm_scratch = off;
+    off = up(off + 2 * nw * FftGeom<512>::SCRATCH_P2 * 8, 128);
+    kp.tc_off_b = off;
+    off += kFtBufs * kFtTileBytes;
+    kp.tc_off_ctrl = off;
+    off += 4 * FT_WORDS;
+    kp.tc_b_src = e->ft_w_off;
+    kp.tc_b_bytes = e->ft_w_bytes;
+    kp.tc_ne = e->ft_mid_slot;                                                           // which edge bin's K slot carries bin 128
+    kp.tc_p_magic = (unsigned)((0x100000000ULL + (unsigned long long)P - 1) / (unsigned long long)P);
+    *smem_out = up(off, 16);
+    return *smem_out <= di.smem_optin;
+}
+
 template <int NFFT, typename SAMP>
 static int launch_staged(const KParams& kp, int dev, int grid, int threads, int smem_bytes, cudaStream_t st) {
     auto kern = srfe_spec_staged_kernel<NFFT, SAMP>;
@@ -403,8 +485,8 @@ struct Config { int warps, ctas, cpc, smem, scratch, tile, ctile_off, blob, dct_
 
 // Launch-shape overrides (srfe_set_tuning; 0 = automatic).  A test / tuning hook: results never depend on them
 // (tests/test_parity_gpu.py::test_results_do_not_depend_on_launch_configuration); no environment is read on the hot path.
-enum Tuning { TUNE_WARPS = 0, TUNE_CTAS, TUNE_CPC, TUNE_DCT_CB, TUNE_DCT_PQ, TUNE_MFCC_TC, TUNE_STAGE, TUNE_COUNT };
-static const char* const kTuningNames[TUNE_COUNT] = {"warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc", "stage"};
+enum Tuning { TUNE_WARPS = 0, TUNE_CTAS, TUNE_CPC, TUNE_DCT_CB, TUNE_DCT_PQ, TUNE_MFCC_TC, TUNE_STAGE, TUNE_FBANK_TC, TUNE_COUNT };
+static const char* const kTuningNames[TUNE_COUNT] = {"warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc", "stage", "fbank_tc"};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static int tune(int which) { return g_tune[which].load(std::memory_order_relaxed); }
 
@@ -475,9 +557,10 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
             const int smem = smem_plan(e, kp, warps, budget, &pl);
             if (smem < 0 || smem > budget) continue;
             for (int cpc = 1; cpc <= cpc_max; ++cpc) {
-                // small batches: never trade CTAs for clips per group (8 clips as one group would run on one SM)
+                // small batches: trading CTAs for clips per group is paid for by the wave factor below (8 clips as one group
+                // would run on one SM: 1 / slots), but a grid that is ALMOST full may be the best cut -- 1,024 clips as 147
+                // groups of 7 finish after 7 clips' time, as 171 groups of 6 only after 12
                 const long long groups = ((long long)kp.n_clips + cpc - 1) / cpc, slots = (long long)di.sms * ctas;
-                if (cpc > 1 && groups < slots) break;
                 const long long nf = (long long)cpc * kp.T, per_round = 4LL * warps;
                 const long long rounds = (nf + per_round - 1) / per_round;
                 // Fitted to scripts/tune.py sweeps on the B200 (profiles/r1_notes.md): throughput ~ round efficiency x
@@ -492,7 +575,7 @@ static int pick_config(const Entry* e, const KParams& kp, const DevInfo& di, Con
                 const bool mf = e->family == FAM_MFCC;
                 double eff = (double)nf / (double)(rounds * per_round);
                 if (mf && ctas == 2) eff = std::sqrt(eff);
-                if (groups >= slots) eff *= (double)groups / (double)(((groups + slots - 1) / slots) * slots);
+                eff *= (double)groups / (double)(((groups + slots - 1) / slots) * slots);
                 double score = eff * std::pow(std::max(1.0, (double)(ctas * warps) - 2.3), 0.8);
                 if (ctas == 2) score *= mf ? 1.6 : ft ? 1.1 : 0.92;
                 score *= ft ? 1.0 - 0.03 * std::log2((double)cpc) : 1.0 + 0.01 * std::log2((double)cpc);
@@ -557,6 +640,28 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
 #undef SRFE_GO_TC
         } else if (tune(TUNE_MFCC_TC) == 2) {
             return fail(SRFE_ERR_UNSUPPORTED, "mfcc_tc = 2: this parameter set / clip length does not fit the tcgen05 MFCC kernel");
+        }
+    }
+    // FBANK: the tcgen05 kernel (filter projection as bf16 hi / mid MMAs, weights resident in TMEM, srfe_fbank_tc.cuh).
+    // Measured against the classic kernel on the B200 (M clips/s, classic / tcgen05): R-FBANK 15.1 / 14.5 at 1,024 clips,
+    // 17.4 / 17.4 at 4,096, 18.4 / 18.5 at 16,384; C-FBANK (40 filters: two of the four read-out quadrants idle) 16.5 / 15.6,
+    // 17.7 / 18.0, 18.5 / 19.2; below ~1,000 clips the classic kernel wins by 5-15 % (pipeline fill per CTA).  A tie -- and
+    // the two kernels agree to 1.4e-4, not bit for bit, so a batch-size rule would make a clip's features depend on the batch
+    // (or shard) it arrives in, which the product promises they never do (test_large_batch_properties,
+    // test_shards_concatenate_bit_exact).  Hence OPT-IN only: srfe_set_tuning("fbank_tc", 2); 0 / 1 = the classic kernel.
+    if (e->family == FAM_FBANK && tune(TUNE_FBANK_TC) == 2) {
+        int smem_ft = 0;
+        KParams kt = kp;
+        if (plan_ft(e, kt, *di, &smem_ft)) {
+            const int grid = std::min(kt.n_clips, di->sms);
+#define SRFE_GO_FT(JLO, JHI)                                                                                     \
+    return i16 ? launch_ft<JLO, JHI, short>(kt, di->index, grid, smem_ft, st)                                     \
+               : launch_ft<JLO, JHI, float>(kt, di->index, grid, smem_ft, st)
+            if (jlo == 0 && jhi <= 13) SRFE_GO_FT(0, 13);
+            SRFE_GO_FT(0, 16);
+#undef SRFE_GO_FT
+        } else {
+            return fail(SRFE_ERR_UNSUPPORTED, "fbank_tc = 2: this parameter set does not fit the tcgen05 FBANK kernel");
         }
     }
     Config cfg;

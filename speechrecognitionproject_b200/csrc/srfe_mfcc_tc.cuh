@@ -76,6 +76,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint32_t a_tmem, ui
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool tc_elect_one() {        // one lane of the (converged) warp; ptxas then issues single-thread code without a per-instruction election loop
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred) :: "memory");
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {

@@ -139,7 +139,7 @@ def launch_count() -> int:
     return int(_lib.lib().srfe_launch_count())
 
 
-_TUNING_KNOBS = ("warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc", "stage")
+_TUNING_KNOBS = ("warps", "ctas", "cpc", "dct_cb", "dct_pq", "mfcc_tc", "stage", "fbank_tc")
 
 
 def set_tuning(**knobs: int) -> None:

@@ -578,6 +578,81 @@ def test_mfcc_tensor_core_kernel_limits(srfe_lib):
         S.set_tuning()
 
 
+FT_CASES = [
+    ("R-FBANK", {}), ("C-FBANK", {}), ("R-FBANK", {"nfilt": 26}), ("R-FBANK", {"nfilt": 128}), ("R-FBANK", {"nfilt": 64, "preemph": 0.0}),
+    ("R-FBANK", {"frame_len": 512, "frame_step": 128, "nfilt": 80}), ("R-FBANK", {"vtlp_alpha": 0.9}), ("C-FBANK", {"vtlp_alpha": 1.08}),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(FT_CASES)))
+def test_fbank_tensor_core_kernel_vs_classic_and_oracle(srfe_lib, idx):
+    """srfe_fbank_tc_kernel (filter projection as bf16 hi/mid tcgen05 MMAs, weights resident in TMEM) against the classic
+    CUDA-core kernel and the float64 oracle: presets, other bank sizes / framings (window 512 = the generic instantiation),
+    VTLP-warped banks, batch sizes that leave CTAs with 1, 2 and 3 clips and partly filled tiles, clip lengths with an odd
+    frame count, int16 ingest."""
+    name, over = FT_CASES[idx]
+    p = replace(S.PRESETS[name], **over)
+    x = oracle.synthetic_corpus(333, config_index=11)
+    x[5] = 0.0                                               # digital silence: every band sum is an exact zero -> eps
+    x[6, 8000:] = 0.0
+    xd = torch.from_numpy(x).cuda()
+    try:
+        for n in (1, 2, 7, 148, 149, 333):
+            S.set_tuning(fbank_tc=2)
+            tc = S.fbank(xd[:n], p)
+            tc2 = S.fbank(xd[:n], p)
+            S.set_tuning(fbank_tc=1)
+            classic = S.fbank(xd[:n], p)
+            assert torch.equal(tc, tc2), "tcgen05 kernel is not deterministic"
+            assert torch.equal(tc[5:6], classic[5:6]) or n <= 5            # exact zeros: bit-identical
+            inside = classic > classic.amax(dim=(1, 2), keepdim=True) - 100.0
+            assert float((tc - classic).abs()[inside].max()) <= 4e-4, (name, over, n)
+        for n_samples in (15840, 15700, 1000, 640):          # odd frame counts repeat the last frame in the pair stream
+            xs = xd[:9, :n_samples].contiguous()
+            S.set_tuning(fbank_tc=2)
+            tc = S.fbank(xs, p)
+            S.set_tuning(fbank_tc=1)
+            classic = S.fbank(xs, p)
+            assert tc.shape == classic.shape
+            inside = classic > classic.amax(dim=(1, 2), keepdim=True) - 100.0
+            assert float((tc - classic).abs()[inside].max()) <= 4e-4, (name, over, n_samples)
+        S.set_tuning(fbank_tc=2)
+        got = S.fbank(xd[:12], p).cpu().numpy()
+        truth = H.oracle_batch(oracle.fbank_truth, x[:12], H.to_oracle_params(p))
+        H.check_logmel(got, truth, f"tc {name} {over}")
+        got16 = S.fbank(xd[:12].to(torch.int16), p).cpu().numpy()
+        np.testing.assert_array_equal(got16, got)
+    finally:
+        S.set_tuning()
+
+
+def test_fbank_tensor_core_kernel_limits(srfe_lib, corpus):
+    """Parameter sets the tcgen05 FBANK kernel does not take (n_fft 640, more than 128 filters) stay on the classic kernel
+    silently and are refused when it is forced; the default dispatch is always the classic kernel (opt-in only)."""
+    x = torch.from_numpy(np.concatenate([corpus] * 200)[:4200]).cuda()
+    try:
+        for p in (S.FbankParams(nfft=640, frame_len=640, frame_step=320, nfilt=80), S.FbankParams(nfilt=200)):
+            S.set_tuning()
+            y = S.fbank(x[:20], p)
+            S.set_tuning(fbank_tc=2)
+            with pytest.raises(RuntimeError, match="SRFE_ERR_UNSUPPORTED"):
+                S.fbank(x[:20], p)
+            S.set_tuning(fbank_tc=1)
+            assert torch.equal(S.fbank(x[:20], p), y)
+        for p in (S.R_FBANK, S.C_FBANK):                     # never dispatched automatically: a clip's features must not
+            for n in (20, 4200):                             # depend on the batch it arrives in (the kernels agree to 1.4e-4)
+                S.set_tuning()
+                y = S.fbank(x[:n], p)
+                S.set_tuning(fbank_tc=1)
+                assert torch.equal(S.fbank(x[:n], p), y)
+                S.set_tuning(fbank_tc=2)
+                b = S.fbank(x[:n], p)
+                inside = y > y.amax(dim=(1, 2), keepdim=True) - 100.0
+                assert float((y - b).abs()[inside].max()) <= 4e-4
+    finally:
+        S.set_tuning()
+
+
 @pytest.mark.parametrize("alpha", [0.9, 1.0, 1.08])
 def test_fbank_vtlp_warped_bank(srfe_lib, corpus, alpha):
     """the VTLP warp of legacy/model_8/dataset_top.py:251-252 as a filter-bank option (one alpha per call)."""
