@@ -616,10 +616,13 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
     const int jlo = kp.w_lo / 32, jhi = (kp.w_hi + 31) / 32;
     const bool a400 = e->mel_ng == 8 && e->mel_code == 0xa400u, e500 = e->mel_ng == 8 && e->mel_code == 0xe500u;
     // MFCC: the tcgen05 kernel when the parameter set and clip length fit it (n_mels % 16 == 0, <= 128 frames, 112 with
-    // deltas) and the clip fills more than half of the 128-row MMA tile -- below that (e.g. the reference's 51-frame clips)
-    // the classic kernel measured faster (B200, 16,384 clips: R-MFCC 15.6 vs 14.4 M clips/s; C-MFCC 11.5 vs 14.9; with two
-    // deltas 9.7 vs 12.4).  srfe_set_tuning("mfcc_tc", 1 | 2) forces either.
-    if (e->family == FAM_MFCC && tune(TUNE_MFCC_TC) != 1 && (kp.T > 64 || tune(TUNE_MFCC_TC) == 2)) {
+    // deltas) and the clip has at least 48 frames.  Measured on the B200 (16,384 clips, M clips/s, classic / tcgen05, after
+    // the read-out warps stopped polling in parallel): R-MFCC parameters at 32 / 40 / 51 / 64 / 101 frames 26.0 / 20.3,
+    // 18.0 / 20.1, 15.7 / 17.0, 13.8 / 15.0, 8.5 / 10.2; C-MFCC parameters 32.5 / 23.2, 23.1 / 22.3, 20.8 / 21.3, 19.2 / 20.5,
+    // 11.5 / 15.0 -- short clips fill too little of the 128-row MMA tile.  The rule depends on the clip length only, never on
+    // the batch size (a clip's features must not depend on its batch); at 64 clips per call the classic kernel is the
+    // quicker one by ~5 us.  srfe_set_tuning("mfcc_tc", 1 | 2) forces either.
+    if (e->family == FAM_MFCC && tune(TUNE_MFCC_TC) != 1 && (kp.T >= 48 || tune(TUNE_MFCC_TC) == 2)) {
         int smem_tc = 0;
         KParams kt = kp;
         if (plan_tc(e, kt, *di, &smem_tc)) {
