@@ -16,6 +16,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/srfe.h"
 #include "srfe_kernels.cuh"
@@ -919,7 +922,33 @@ static bool is_pageable(const void* host_ptr) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-// rows of `row_bytes` from a strided source into a dense destination, split over a few host threads (one memcpy
+// Large staging copies with non-temporal stores: the destination (a pinned staging buffer on the way in, the caller's
+// result buffer on the way out) is not read again by this core, and a cached store would first fetch every destination
+// line (read-for-ownership): 3 bytes of memory traffic per byte copied instead of 2.  glibc's memcpy only switches to
+// streaming stores above a per-call size the per-thread slices here never reach.
+static void copy_stream(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+    if (n >= (size_t)(256u << 10)) {
+        size_t head = (size_t)((16 - ((uintptr_t)dst & 15)) & 15);
+        if (head) { std::memcpy(dst, src, head); dst += head; src += head; n -= head; }
+        const size_t blocks = n / 64;
+        for (size_t i = 0; i < blocks; ++i) {
+            const __m128i a = _mm_loadu_si128((const __m128i*)(src) + 0), b = _mm_loadu_si128((const __m128i*)(src) + 1);
+            const __m128i c = _mm_loadu_si128((const __m128i*)(src) + 2), d = _mm_loadu_si128((const __m128i*)(src) + 3);
+            _mm_stream_si128((__m128i*)(dst) + 0, a); _mm_stream_si128((__m128i*)(dst) + 1, b);
+            _mm_stream_si128((__m128i*)(dst) + 2, c); _mm_stream_si128((__m128i*)(dst) + 3, d);
+            src += 64; dst += 64;
+        }
+        n -= blocks * 64;
+        if (n) std::memcpy(dst, src, n);
+        _mm_sfence();
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
+
+// rows of `row_bytes` from a strided source into a dense destination, split over a few host threads (one copy
 // stream per thread: a single core moves ~10 GB/s, the PCIe link ~50)
 static void gather_rows(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_stride_bytes) {
     const size_t total = rows * row_bytes;
@@ -927,7 +956,7 @@ static void gather_rows(char* dst, const char* src, size_t rows, size_t row_byte
     nthr = std::max(1u, std::min(nthr ? nthr / 2 : 1u, 8u));
     if (total < (size_t)(4u << 20)) nthr = 1;
     auto work = [=](size_t r0, size_t r1) {
-        if (src_stride_bytes == row_bytes) std::memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
+        if (src_stride_bytes == row_bytes) copy_stream(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
         else for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * row_bytes, src + r * src_stride_bytes, row_bytes);
     };
     if (nthr == 1) { work(0, rows); return; }
