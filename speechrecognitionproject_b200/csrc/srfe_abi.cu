@@ -371,9 +371,9 @@ static int launch_k(const KParams& kp, int dev, int grid, int threads, int smem_
     return SRFE_OK;
 }
 
-template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
+template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP, int MB = 1>
 static int launch_tc(const KParams& kp, int dev, int grid, int smem_bytes, cudaStream_t st) {
-    auto kern = srfe_mfcc_tc_kernel<NFFT, JLO, JHI, NG, CODE, SAMP>;
+    auto kern = srfe_mfcc_tc_kernel<NFFT, JLO, JHI, NG, CODE, SAMP, MB>;
     static std::atomic<int> attr_set[kMaxDevices];
     if (attr_set[dev].load(std::memory_order_acquire) < smem_bytes) {
         SRFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -630,18 +630,22 @@ static int launch(const Entry* e, KParams kp, bool i16, cudaStream_t st) {
         KParams kt = kp;
         if (plan_tc(e, kt, *di, &smem_tc)) {
             const int grid = std::min(kt.n_clips, di->sms);
-#define SRFE_GO_TC(N, JLO, JHI, NG, CODE)                                                                        \
-    return i16 ? launch_tc<N, JLO, JHI, NG, CODE, short>(kt, di->index, grid, smem_tc, st)                       \
-               : launch_tc<N, JLO, JHI, NG, CODE, float>(kt, di->index, grid, smem_tc, st)
+#define SRFE_GO_TC(N, JLO, JHI, NG, CODE, MB)                                                                    \
+    return i16 ? launch_tc<N, JLO, JHI, NG, CODE, short, MB>(kt, di->index, grid, smem_tc, st)                   \
+               : launch_tc<N, JLO, JHI, NG, CODE, float, MB>(kt, di->index, grid, smem_tc, st)
+            // mel batch (mel_project): all eight band-sum groups before their emits when the frame warps set the pace
+            // (no deltas: +2.5 % on the headline shape), one group at a time when the read-out warps do (deltas)
             if (e->n_fft == 512) {
                 if (jlo >= 1 && jhi <= 15) {
-                    if (a400) SRFE_GO_TC(512, 1, 15, 8, 0xa400u);
-                    SRFE_GO_TC(512, 1, 15, 0, 0u);
+                    if (a400 && kt.n_deltas == 0) SRFE_GO_TC(512, 1, 15, 8, 0xa400u, 8);
+                    if (a400) SRFE_GO_TC(512, 1, 15, 8, 0xa400u, 1);
+                    SRFE_GO_TC(512, 1, 15, 0, 0u, 1);
                 }
-                SRFE_GO_TC(512, 0, 16, 0, 0u);
+                SRFE_GO_TC(512, 0, 16, 0, 0u, 1);
             } else {
-                if (e500) SRFE_GO_TC(640, 0, 20, 8, 0xe500u);
-                SRFE_GO_TC(640, 0, 20, 0, 0u);
+                if (e500 && kt.n_deltas == 0) SRFE_GO_TC(640, 0, 20, 8, 0xe500u, 8);
+                if (e500) SRFE_GO_TC(640, 0, 20, 8, 0xe500u, 1);
+                SRFE_GO_TC(640, 0, 20, 0, 0u, 1);
             }
 #undef SRFE_GO_TC
         } else if (tune(TUNE_MFCC_TC) == 2) {

@@ -314,30 +314,44 @@ __device__ __forceinline__ P2 pair_power(const KParams& p, const SAMP* __restric
 // count per group (ELL); emit(m, acc, guard) receives filter m's (frame A, frame B) sums.
 //   NG / CODE: compile-time bank shape (NG groups, 2 bits per group = float4 steps - 1), 0 = runtime metadata
 // --------------------------------------------------------------------------------
-template <int NG, unsigned CODE, typename Emit>
+template <int NG, unsigned CODE, int BATCH = 1, typename Emit>
 __device__ __forceinline__ void mel_project(const P2* pbuf, const int2* g_meta, int n_fgroups, const int* f_start,
                                             const float2* f_w2, int l, Emit emit) {
     if (NG > 0) {
+        // BATCH groups at a time: first their band sums (independent accumulator chains the scheduler can interleave), then
+        // their emits.  With emit() inside the group loop (BATCH = 1) every group's power reads wait for the previous group's
+        // shared-memory store (the compiler must assume they alias): eight load -> 16-deep FFMA2 chain -> log -> store
+        // sequences in a row per frame pair.  Same arithmetic in the same order either way (bit-identical results).
+        // Measured (B200, tcgen05 MFCC kernel, BATCH 1 / 2 / 4 / 8): C-MFCC 15.24 / 15.42 / 15.57 / 15.63 M clips/s at 262,144
+        // clips -- but C-MFCC-D2 11.79 / 11.20 / 11.24 / 11.11 and R-MFCC 17.1 / 16.6 / 16.6 / 16.8: where the read-out warps
+        // set the pace (deltas), burstier frame warps take issue slots from them.  The dispatcher picks per launch.
+        constexpr int HALF = NG > BATCH ? BATCH : (NG > 0 ? NG : 1);
         int off4 = 0;                       // all of this folds at compile time
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
-            const int m = 16 * i + l;
-            const P2* pq = pbuf + f_start[m];
-            const float2* wq = f_w2 + off4 * 32 + l;
-            P2 acc = bc(0.f);
+        for (int h0 = 0; h0 < NG; h0 += HALF) {
+            P2 accs[HALF];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                if (q4 < n4) {
-                    const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
-                    acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
-                    acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
-                    acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
-                    acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
+            for (int i = h0; i < h0 + HALF && i < NG; ++i) {
+                const int n4 = (int)((CODE >> (2 * i)) & 3u) + 1;
+                const int m = 16 * i + l;
+                const P2* pq = pbuf + f_start[m];
+                const float2* wq = f_w2 + off4 * 32 + l;
+                P2 acc = bc(0.f);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    if (q4 < n4) {
+                        const float2 wa = wq[q4 * 32], wb = wq[q4 * 32 + 16];
+                        acc = pfma(pq[4 * q4 + 0], bc(wa.x), acc);
+                        acc = pfma(pq[4 * q4 + 1], bc(wa.y), acc);
+                        acc = pfma(pq[4 * q4 + 2], bc(wb.x), acc);
+                        acc = pfma(pq[4 * q4 + 3], bc(wb.y), acc);
+                    }
                 }
+                off4 += n4;
+                accs[i - h0] = acc;
             }
-            off4 += n4;
-            emit(m, acc, i == NG - 1);
+#pragma unroll
+            for (int i = h0; i < h0 + HALF && i < NG; ++i) emit(16 * i + l, accs[i - h0], i == NG - 1);
         }
     } else {
         for (int i = 0; i < n_fgroups; ++i) {

@@ -89,7 +89,7 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP>
+template <int NFFT, int JLO, int JHI, int NG, unsigned CODE, typename SAMP, int MB = 1>
 __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KParams p) {
     constexpr int FAM = FAM_MFCC;
     typedef FftGeom<NFFT> G;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) srfe_mfcc_tc_kernel(const KPara
             run_max = fmaxf(run_max, fmaxf(da, db));
             fsum = padd(fsum, mkp(da, db));
         };
-        mel_project<NG, CODE>(pbuf, g_meta, p.n_fgroups, f_start, f_w2, l, emit);
+        mel_project<NG, CODE, MB>(pbuf, g_meta, p.n_fgroups, f_start, f_w2, l, emit);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
             fsum.lo += __shfl_xor_sync(0xffffffffu, fsum.lo, o);
