@@ -410,6 +410,7 @@ static bool plan_tc(const Entry* e, KParams& kp, const DevInfo& di, int* smem_ou
     int ring = std::min(2 * P, left / row_bytes - 1);
     if (ring < P + 8) return false;
     kp.tc_ring = ring;
+    kp.tc_early = ring >= 4 * nw + P ? 1 : 0;                          // room for two pairs per half-warp in flight plus a clip
     off += (ring + 1) * kp.tile_stride * 8;
     kp.tc_off_fmean = off;
     off = up(off + (ring + 1) * 8, 16);

@@ -77,6 +77,7 @@ struct KParams {
     int tc_ne, tc_no, tc_tmem_cols;            // accumulator widths (even / odd coefficients, multiples of 16), TMEM columns to allocate
     int tc_ring, tc_off_fmean, tc_off_ctrl;    // ring capacity in pair rows, per-row frame means, control block
     unsigned tc_ring_magic, tc_p_magic;        // ceil(2^32 / RING), ceil(2^32 / pairs per clip)
+    int tc_early;                              // frame warps claim their next pair one iteration ahead (ring permitting)
 };
 
 // --------------------------------------------------------------------------------
