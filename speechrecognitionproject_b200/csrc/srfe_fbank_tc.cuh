@@ -62,13 +62,6 @@ __device__ __forceinline__ void ft_mma_bf16(uint32_t d_tmem, uint32_t a_tmem, ui
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void ft_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // one 16-byte chunk (8 K elements = this lane's slots r = 0 .. 7 of one frame) as bf16 hi and bf16 mid
 template <bool HI_HALF>
@@ -96,6 +89,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) srfe_fbank_tc_kernel(const KPar
     const int FW = (nthr >> 5) - kTcEpiWarps;               // frame warps
 
     {   // FFT tables -> shared memory (the sparse mel tables of the classic kernel are not needed); tile buffers zeroed once
+        // (rows past the end of the last, partly filled tile are never written: their columns of D are never read either)
         const int4* src = reinterpret_cast<const int4*>(p.blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = tid; i < p.blob_bytes / 16; i += nthr) dst[i] = __ldg(src + i);
