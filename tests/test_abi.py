@@ -34,6 +34,18 @@ def test_header_symbols_all_exported(srfe_lib):
     assert srfe_lib.srfe_version() == 1
 
 
+def test_tuning_knobs_agree_between_header_python_and_library(srfe_lib):
+    """Every knob the Python mirror knows is documented in include/srfe.h and accepted by srfe_set_tuning (host-side only:
+    the hook stores an integer); unknown names are refused."""
+    from speechrecognitionproject_b200 import features as F
+    hdr = open(os.path.join(ROOT, "include", "srfe.h")).read()
+    doc = hdr[hdr.index("Launch-shape override"):hdr.index("int srfe_set_tuning")]
+    for k in F._TUNING_KNOBS:
+        assert f'"{k}"' in doc, f"tuning knob {k} is not documented in include/srfe.h"
+        assert srfe_lib.srfe_set_tuning(k.encode(), 0) == 0
+    assert srfe_lib.srfe_set_tuning(b"no_such_knob", 1) != 0
+
+
 def test_out_shapes_and_bytes(srfe_lib):
     expect = {"R-SPEC": ((321, 49), 126916), "C-SPEC": ((257, 61), 126708), "R-FBANK": ((98, 120), 111040),
               "C-FBANK": ((98, 40), 79680), "R-MFCC": ((39, 51), 71956), "C-MFCC": ((40, 101), 80160)}
