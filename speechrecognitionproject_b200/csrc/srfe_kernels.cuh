@@ -152,6 +152,27 @@ __device__ __forceinline__ void fetch_frame(const KParams& p, const S* __restric
     }
 }
 
+// Frame B of a pair when it starts HS * 32 samples after frame A in the same clip (hop = 160 = 5 x 32 for the filter-bank
+// presets): lane l's sample pair (l, j) of B is the pair (l, j + HS) of A, so only B's last HS pairs (and, for FBANK, the
+// samples before them) are loaded: 36 instead of 52 loads per lane and frame pair.
+template <int FAM, int JLO, int JHI, int HS, typename S>
+__device__ __forceinline__ void fetch_frame_after(const KParams& p, const S* __restrict__ x, int base, int l,
+                                                  const RawFrame<FAM, JHI - JLO>& ra, RawFrame<FAM, JHI - JLO>& rb) {
+    constexpr int NJ = JHI - JLO;
+    rb.final_ = false;
+    const S* xs = x + base + 2 * l;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+        if (i + HS < NJ) {
+            rb.s[i] = ra.s[i + HS];
+            if (FAM == FAM_FBANK) rb.prev[i] = ra.prev[i + HS];
+        } else {
+            rb.s[i] = ld2<S>(xs + 32 * (i + JLO));
+            if (FAM == FAM_FBANK) rb.prev[i] = ld1<S>(xs + 32 * (i + JLO) - 1);       // base > 0 here: never the clip's first sample
+        }
+    }
+}
+
 template <int FAM, int NJ>
 __device__ __forceinline__ void emphasise(const KParams& p, const RawFrame<FAM, NJ>& r, int j, float& s0, float& s1) {
     s0 = r.s[j].x;
@@ -276,7 +297,14 @@ __device__ __forceinline__ P2 pair_power(const KParams& p, const SAMP* __restric
     //  the first use of the samples stays at ~6 % of warp time.)
     RawFrame<FAM, NJ> rawA, rawB;
     fetch_frame<FAM, JLO, JHI, SAMP, SMEM>(p, clipA, baseA, l, rawA);
-    fetch_frame<FAM, JLO, JHI, SAMP, SMEM>(p, clipB, baseB, l, rawB);
+    // FBANK only (its frames cost two loads per sample pair: the pair and the sample before it).  Measured on the B200 with the
+    // sharing enabled for every family (16,384 clips, M clips/s): R-FBANK 18.35 -> 19.43, C-FBANK 18.41 -> 19.17, R-SPEC TF 26.8 ->
+    // 27.3, but C-SPEC TF 35.2 -> 33.7, C-MFCC 15.24 -> 14.57, R-MFCC 17.2 -> 15.8: there the copies and the branch cost more
+    // than the loads they replace (which hit L1 anyway).
+    const bool after = FAM == FAM_FBANK && !SMEM && clipA == clipB && !rawA.final_ && baseB - baseA == 160 && 5 < NJ &&
+                       baseB + 32 * JHI <= p.n_samples;
+    if (after) fetch_frame_after<FAM, JLO, JHI, 5, SAMP>(p, clipB, baseB, l, rawA, rawB);
+    else fetch_frame<FAM, JLO, JHI, SAMP, SMEM>(p, clipB, baseB, l, rawB);
     C2 v[G::V];
     window_pair<NFFT, FAM, JLO, JHI>(p, rawA, rawB, l, s_win, v);
     after_fetch();
